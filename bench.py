@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Headline benchmark: GBM path-steps/s (and CF estimates/s) of the batch-generation hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic contracts: Philox normals ->
+GBM stepping -> payoff -> FFT/mean, i.e. one CF training target per contract
+(reference: gbm_trainer.py:1546-1553 for one `_run_batch`).
+
+Workload (BASELINE.json configs[1], "c2"): fp32, 1 contract (X0=100,K=100,T=1,r=.05,d=0,v=.2),
+252 timesteps, network_size=128, batches_per_mc_run=65 536 per GPU, RAW, LOG_EULER.
+Multi-GPU: weak scaling — every rank simulates 65 536 batch rows of the same contract batch
+(global path counters, B_total = 65 536 * N), then ONE NCCL all-reduce of the complex partial CF
+sums.
+
+The JSON line carries: `value` (device-resident inputs, kernel-only), `e2e` (host buffers through
+the C-ABI host entry point: pinned H2D of the contracts, D2H of the targets, inside the timed
+region), `roofline` for the dominant kernel (the fused simulator: bound by FP32-issue/XU pipes, not
+HBM or tensor — peaks calibrated live by two microbenchmarks), `roofline_materialised` (the
+HBM-bound generator and stepper of the materialised-normals mode against MEASURED_PEAKS.json),
+`cpu_baseline` (the oracle port on the host cores, bounded sample) and `clocks`.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CANON = (100.0, 100.0, 1.0, 0.05, 0.0, 0.2)  # reference tests/test_gbm.py:146
+WORKLOADS = {
+    # name: (contracts, timesteps, network_size, batches per GPU, dtype)
+    "c2": dict(contracts=1, T=252, N=128, B=65536, dtype="float32"),
+    "c2x8": dict(contracts=8, T=252, N=128, B=65536, dtype="float32"),
+    "c3_trainer": dict(contracts=1024, T=1, N=16, B=4096, dtype="float32"),
+    "c4": dict(contracts=512, T=365, N=256, B=4096, dtype="float64"),
+}
+# SASS-counted work per fp32 path-step of the fused log-Euler kernel (profiles/ has the listing):
+ISSUE_SLOTS_PER_STEP = 17.75  # warp-instructions issued per path-step (per lane: lane-ops)
+XU_OPS_PER_STEP = 2.0  # (LG2 + SQRT + SIN + COS) per Box–Muller pair / 2 normals; log-sum variant
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    import numpy as np
+
+    from oracle import gbm as ogbm
+    from oracle import philox
+
+    T, N, b_lo, b_hi, seed, k, dtype = job
+    z = philox.normals_matrix(T, N * (b_hi - b_lo), np.dtype(dtype), seed, k)  # this worker's own slice
+    c = ogbm.Contract(*CANON)
+    sr = ogbm.simulate(c, z, normalization=ogbm.RAW)
+    pr = ogbm.price(c, sr)
+    return np.fft.fft(pr.put_price.reshape(b_hi - b_lo, N), axis=1).sum(axis=0)
+
+
+def cpu_path(T: int, N: int, B: int, dtype: str, cores: int, pool) -> float:
+    """One pass of the oracle over B batch rows (normals + stepping + payoff + FFT/mean), split
+    over `cores` worker processes.  Returns seconds."""
+    import numpy as np
+
+    cuts = np.linspace(0, B, cores + 1).astype(int)
+    jobs = [(T, N, int(lo), int(hi), 7, i, dtype) for i, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])) if hi > lo]
+    t0 = time.perf_counter()
+    parts = pool.map(_cpu_worker, jobs)
+    _ = sum(parts) / B
+    return time.perf_counter() - t0
+
+
+def run_reference(args) -> None:
+    """--impl reference: the reference's algorithm on the host cores (the reference itself is
+    GPU-only Python/Numba/CuPy and cannot run without CuPy) — the oracle port,
+    all cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample_B = args.cpu_sample_batches or max(cores * 8, 256)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(max(args.warmup, 1)):
+            cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
+        times = [cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool) for _ in range(args.steps)]
+    total = sum(times)
+    steps_done = args.steps * sample_B * w["N"] * w["T"]
+    value = steps_done / total
+    sample = f"{sample_B} of {w['B']} batch rows per step ({sample_B * w['N']} paths x {w['T']} steps), oracle NumPy port, fork pool"
+    line = {
+        "impl": "reference", "metric": "gbm_path_steps_per_sec", "value": value, "unit": "path-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if w["dtype"] == "float32" else "f64",
+        "data": "synthetic", "config": workload_config(args.workload, args.gpus),
+        "cpu_baseline": {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "path-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cf_estimates_per_sec": value / (w["B"] * w["N"] * w["T"]),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name: str, gpus: int) -> dict:
+    w = WORKLOADS[name]
+    return {
+        "workload": f"{name}: {w['contracts']} contract(s) {w['dtype']}, T={w['T']}, N={w['N']}, B={w['B']} per GPU, RAW, LOG_EULER, fused Philox normals",
+        "contracts_per_step": w["contracts"], "timesteps": w["T"], "network_size": w["N"],
+        "batches_per_gpu": w["B"], "batches_total": w["B"] * gpus, "parallelism": f"batch-shard x{gpus} + 1 allreduce" if gpus > 1 else "single GPU",
+        "l2": "fused mode has no HBM-resident inputs (normals are drawn in registers); a 256 MiB L2 flush runs between timed steps anyway; materialised-mode inputs (8.5 GB) exceed L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+def run_b200(args) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from spectralmc_b200 import _cabi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = WORKLOADS[args.workload]
+    dtype = torch.float32 if w["dtype"] == "float32" else torch.float64
+    C, T, N, B = w["contracts"], w["T"], w["N"], w["B"]
+    B_total = B * world
+    rows = np.tile(np.asarray(CANON, dtype=np.float64), (C, 1))
+    if C > 1:  # vary the strike so contracts differ
+        rows[:, 1] = np.linspace(80.0, 120.0, C)
+    contracts_dev = torch.tensor(rows, device=dev)
+    contracts_pin = torch.tensor(rows).pin_memory()
+    out_pin = torch.empty((C, N), dtype=_cabi.complex_dtype(dtype)).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def make_args(step: int, contracts):
+        return _cabi.make_fused_args(contracts, C, T, N, B_total, dtype, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 7, step * C,
+                                     batch_begin=rank * B, batch_end=(rank + 1) * B)
+
+    ws = torch.empty(_cabi.cf_fused_host_workspace_bytes(make_args(0, None)) + 4096, dtype=torch.uint8, device=dev)
+    launches = {"n": 0}
+    plan_launches = int(_cabi.LIB.smc_cf_fused_launch_count(_cabi.byref(make_args(0, None))))
+
+    def step_device(step: int):
+        out = _cabi.cf_fused(make_args(step, contracts_dev), dev, dtype, ws)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(out))
+        launches["n"] += plan_launches
+        return out
+
+    def step_e2e(step: int):
+        if world == 1:
+            _cabi.cf_fused_host(make_args(step, None), contracts_pin, out_pin, ws)  # H2D + kernels + D2H + sync
+        else:
+            cdev = contracts_pin.to(dev, non_blocking=True)
+            out = _cabi.cf_fused(make_args(step, cdev), dev, dtype, ws)
+            dist.all_reduce(torch.view_as_real(out))
+            out_pin.copy_(out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        launches["n"] += plan_launches
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps: int, first_step: int) -> float:
+        """Sum of per-step CUDA-event durations (ms); L2 flushed between steps, outside the events."""
+        pairs = []
+        barrier()
+        for s in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn(first_step + s)
+            b.record()
+            pairs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in pairs)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for s in range(args.warmup):
+        step_device(s)
+        step_e2e(s)
+    barrier()
+
+    with ClockSampler(local) as clocks:
+        ms_dev = timed(step_device, args.steps, 1000)
+        ms_e2e = timed(step_e2e, args.steps, 2000)
+    clk = clocks.summary()
+
+    path_steps_per_step = float(C) * B_total * N * T
+    value = path_steps_per_step * args.steps / (ms_dev * 1e-3)
+    e2e_value = path_steps_per_step * args.steps / (ms_e2e * 1e-3)
+
+    line = {
+        "metric": "gbm_path_steps_per_sec", "value": value, "unit": "path-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "cf_estimates_per_sec": C * args.steps / (ms_dev * 1e-3),
+        "e2e": {"value": e2e_value, "unit": "path-steps/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(contracts_pin.numel() * 8), "d2h_bytes_per_step": int(out_pin.numel() * out_pin.element_size()),
+                "api": "smc_cf_fused_host (C ABI, pinned host buffers)" if world == 1 else "H2D + smc_cf_fused + ncclAllReduce + D2H"},
+        "gpu_launches": launches["n"], "clocks": clk,
+    }
+
+    if rank == 0:
+        # ---- rooflines (rank 0, after the timed region) ----
+        peaks = measured_peaks()
+        calib = {}
+        for kind, name in ((0, "ffma"), (1, "mufu"), (2, "philox")):
+            ops, ms = _cabi.pipe_calibrate(kind, 1 << 15, dev)
+            calib[name] = ops / (ms * 1e-3)
+        per_gpu_rate = value / world
+        issue_ach = per_gpu_rate * ISSUE_SLOTS_PER_STEP
+        xu_ach = per_gpu_rate * XU_OPS_PER_STEP
+        fr_issue, fr_xu = issue_ach / calib["ffma"], xu_ach / calib["mufu"]
+        bound = "fp32_issue" if fr_issue >= fr_xu else "xu"
+        line["roofline"] = {
+            "kernel": "smc::tile_kernel<float, SRC_FUSED, LOG_EULER, OUT_COLSUM>",
+            "bound": bound,
+            "achieved": (issue_ach if bound == "fp32_issue" else xu_ach) / 1e12,
+            "peak": (calib["ffma"] if bound == "fp32_issue" else calib["mufu"]) / 1e12,
+            "unit": "Tlane-op/s", "frac": max(fr_issue, fr_xu), "traffic": None,
+            "peak_source": "calibrated live: smc_pipe_calibrate (FFMA issue-rate and MUFU.EX2 microbenchmarks); MEASURED_PEAKS.json holds only HBM/bf16",
+            "detail": {"issue_slots_per_path_step": ISSUE_SLOTS_PER_STEP, "xu_ops_per_path_step": XU_OPS_PER_STEP,
+                       "fp32_issue": {"achieved": issue_ach / 1e12, "peak": calib["ffma"] / 1e12, "frac": fr_issue},
+                       "xu": {"achieved": xu_ach / 1e12, "peak": calib["mufu"] / 1e12, "frac": fr_xu},
+                       "philox_blocks_per_s_peak": calib["philox"]},
+        }
+        line["roofline_materialised"] = materialised_roofline(_cabi, torch, dev, peaks, T, N, dtype)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(w, args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def materialised_roofline(_cabi, torch, dev, peaks, T, N, dtype) -> dict:
+    """HBM-bound kernels of the materialised-normals mode, timed alone with CUDA events.
+    Algorithmic bytes: generator sizeof(real)/normal written; in-place stepper 2*sizeof(real)
+    per path-step; terminal-only stepper sizeof(real) per path-step."""
+    B = 16384  # 2.1M paths x 252 steps x 4 B = 2.1 GB per matrix: >> L2
+    P = N * B
+    z = torch.empty((T, P), dtype=dtype, device=dev)
+    size = z.element_size()
+    hbm = peaks.get("hbm_gbs")
+    out = {"peak": hbm, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm else "unavailable", "matrix_bytes": T * P * size}
+
+    def time_it(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); b.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    ms = time_it(lambda: _cabi.philox_normals(z, 7, 0))
+    out["philox_normals"] = {"bound": "hbm", "achieved": T * P * size / ms / 1e6, "ms": ms, "bytes": T * P * size}
+    ms = time_it(lambda: _cabi.gbm_terminal_from_normals(z, 1.0 / T, *CANON[:1], CANON[3], CANON[4], CANON[5], _cabi.SMC_LOG_EULER))
+    out["gbm_terminal_from_normals"] = {"bound": "hbm", "achieved": T * P * size / ms / 1e6, "ms": ms, "bytes": T * P * size}
+    ms = time_it(lambda: _cabi.gbm_paths_inplace(z, 1.0 / T, CANON[0], CANON[3], CANON[4], CANON[5], _cabi.SMC_LOG_EULER, 256))
+    out["gbm_paths_inplace"] = {"bound": "hbm", "achieved": 2 * T * P * size / ms / 1e6, "ms": ms, "bytes": 2 * T * P * size}
+    if hbm:
+        for k in ("philox_normals", "gbm_terminal_from_normals", "gbm_paths_inplace"):
+            out[k]["frac"] = out[k]["achieved"] / hbm
+    del z
+    return out
+
+
+def cpu_baseline(w: dict, args) -> dict:
+    import multiprocessing as mp
+
+    cores = os.cpu_count() or 1
+    sample_B = args.cpu_sample_batches or max(cores * 8, 256)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
+        reps, total = 0, 0.0
+        while total < 10.0 and reps < 50:
+            total += cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
+            reps += 1
+    value = reps * sample_B * w["N"] * w["T"] / total
+    return {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} passes over {sample_B} of {w['B']} batch rows ({sample_B * w['N']} paths x {w['T']} steps each); oracle NumPy port over a {cores}-process fork pool"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-batches", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+/*
+ * spectralmc_b200 — C ABI of the B200-native batch-generation hot path.
+ *
+ * One shared library (libspectralmc_b200.so), plain pointers and sizes only; no
+ * torch / Python types.  The reference (Tuee22/SpectralMC) is 100 % Python and has no
+ * FFI of its own: each entry point below replaces a Python call site of the reference,
+ * cited as file:line under /root/reference/src/spectralmc/.  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add at each seam.
+ *
+ * Conventions
+ *   - every function returns 0 on success, an SMC_E* code otherwise; the message is
+ *     available from smc_last_error() (thread-local).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
+ *     work is stream-ordered; no function synchronises the host unless its name ends in
+ *     `_host`.  The library never allocates device memory: scratch space is a caller-
+ *     provided workspace whose size comes from the matching *_workspace_bytes().
+ *   - `dtype`: SMC_F32 / SMC_F64 (the reference's Precision.float32/float64,
+ *     models/numerical.py:124-130).  Complex outputs are interleaved (re, im) pairs of the
+ *     same width (complex64 / complex128).
+ *   - matrices are C-contiguous (row-major), as the reference's CuPy arrays are.
+ *   - contracts are rows of 6 doubles in the reference's field order X0, K, T, r, d, v
+ *     (gbm.py:267-277).
+ */
+#ifndef SPECTRALMC_B200_H_
+#define SPECTRALMC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMC_VERSION 100 /* 0.1.0 */
+
+enum smc_status {
+  SMC_OK = 0,
+  SMC_EINVAL = 1,      /* bad argument (shape, dtype, enum, alignment)      */
+  SMC_ECUDA = 2,       /* CUDA runtime / launch error (message has details) */
+  SMC_EWORKSPACE = 3,  /* workspace too small                               */
+  SMC_EUNSUPPORTED = 4 /* legal in the reference but not built here         */
+};
+
+enum smc_dtype { SMC_F32 = 0, SMC_F64 = 1 };
+/* effects/montecarlo.py:24-35 */
+enum smc_scheme {
+  SMC_LOG_EULER = 0,   /* PathScheme.LOG_EULER  (gbm.py:245-250)                                  */
+  SMC_SIMPLE_EULER = 1, /* PathScheme.SIMPLE_EULER (gbm.py:251-257)                                */
+  /* fused path only: the same log-Euler mathematics with the exponential taken at EVERY step,
+   * X *= exp(a + b z), exactly as the reference kernel iterates (gbm.py:249).  SMC_LOG_EULER
+   * sums the log-returns and exponentiates once (prod exp(x_j) == exp(sum x_j)); this variant
+   * exists so the two can be measured side by side. */
+  SMC_LOG_EULER_STEPWISE = 2
+};
+enum smc_normalization { SMC_NORMALIZE = 0, SMC_RAW = 1 };
+/* how the CF estimate is formed from the [B, N] payoff matrix */
+enum smc_cf_method {
+  SMC_CF_MEAN_THEN_FFT = 0, /* FFT_n(mean_b mat): one length-N transform (linearity)          */
+  SMC_CF_ROW_FFT = 1        /* mean_b FFT_n(mat[b,:]): a shared-memory/shuffle FFT per row,   */
+                            /* fused with the batch mean (N a power of two, 32 <= N <= 2048)  */
+};
+
+int smc_version(void);
+const char* smc_last_error(void);
+/* SM count / compute capability of the current device (fails loudly without a GPU). */
+int smc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  normal supply — replaces
+ *     cp.random.default_rng(seed).standard_normal((rows, cols), dtype)
+ *     (async_normals.py:214-215; effects/interpreter.py:578-583).
+ * Writes the `matrix_index`-th (rows, cols) standard-normal matrix of stream `seed`
+ * (Philox4x32-10 + Box–Muller; the stream is specified in oracle/philox.py).  Element
+ * (i, j) is a pure function of (seed, matrix_index, i, j).
+ */
+int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
+                       uint64_t matrix_index, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  path kernel — replaces the Numba launch
+ *     SimulateBlackScholes[blocks, threads, stream](io, timesteps, dt, X0, r, d, v, log_flag)
+ *     (gbm.py:224-257, launched at gbm.py:413-426 and effects/interpreter.py:645-654).
+ * `io` holds N(0,1) draws on entry, shape (rows = timesteps, cols = paths); on return
+ * io[i, j] is path j after step i+1.  threads_per_block in {32,...,1024} is honoured as the
+ * CTA size (gbm.py:71).
+ */
+int smc_gbm_paths_inplace(void* io, int64_t rows, int64_t cols, int dtype, double dt, double X0,
+                          double r, double d, double v, int scheme, int threads_per_block,
+                          void* stream);
+
+/* Same stepping, read-only: consumes `normals` (rows, cols) and writes only the terminal
+ * row to `terminal` (cols).  This is the 1x-read HBM-roofline form of K2 used when the
+ * caller needs sims[-1] only (gbm.py:472). */
+int smc_gbm_terminal_from_normals(const void* normals, int64_t rows, int64_t cols, int dtype,
+                                  double dt, double X0, double r, double d, double v, int scheme,
+                                  void* terminal, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4+K5  forward normalisation of every row — replaces
+ *     row_means = cp.mean(sims, axis=1); sims *= expand_dims(forwards / row_means, 1)
+ *     (gbm.py:437-438).  `forwards` is a device vector (rows) of `dtype`.
+ */
+size_t smc_normalize_rows_workspace_bytes(int64_t rows, int64_t cols);
+int smc_normalize_rows(void* sims, int64_t rows, int64_t cols, int dtype, const void* forwards,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K6  payoff — replaces gbm.py:467-474:
+ *     put = df * max(K - terminal, 0); call = df * max(terminal - K, 0)  (arithmetic in dtype)
+ * put / call may be NULL.
+ */
+int smc_payoff(const void* terminal, int64_t n, int dtype, double K, double df, void* put,
+               void* call, void* stream);
+
+/* K11  host-price reduction — replaces the three cp .mean() of gbm.py:496-498 with one
+ * fused, deterministic reduction.  out3 = device double[3]: mean(underlying), mean(put),
+ * mean(call).  Any input may be NULL (its slot is set to 0). */
+size_t smc_means3_workspace_bytes(int64_t n);
+int smc_means3(const void* underlying, const void* put, const void* call, int64_t n, int dtype,
+               double* out3, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K7+K8  CF estimate of a materialised payoff matrix — replaces
+ *     cp.mean(cp.fft.fft(mat, axis=1), axis=0),  mat = put_price.reshape(B, N)
+ *     (gbm_trainer.py:409-412, 814-817; effects/interpreter.py:703).
+ * `mat` is (B, N) real of `dtype`; `out` is N complex of matching width.
+ */
+size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t network_size, int method);
+int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t network_size, int dtype, int method,
+                    void* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused batch path — replaces the whole per-contract Python loop
+ *     [ _simulate_fft(c) for c in sobol_inputs ]  +  cp.asarray(fft_values)
+ *     (gbm_trainer.py:1546-1553  ->  gbm_trainer.py:806-817  ->  gbm.py:450-488,400-447
+ *      ->  async_normals.py:388-396)
+ * with in-register Philox normals, log-Euler / simple-Euler stepping, payoff, column sums and
+ * one FFT per contract.  Contract c consumes normal matrix `first_matrix_index + c`, exactly
+ * as C successive BlackScholes.price() calls consume C matrices (gbm.py:405).
+ *
+ * Sharding (multi-GPU): a rank simulates batch rows [batch_begin, batch_end) of every
+ * contract; Philox counters use the GLOBAL path index b*N + n, so the union over ranks equals
+ * the single-GPU result up to summation order.  Outputs are PARTIAL: cf_out holds
+ * (1/batches_total) * sum over the local rows, so a sum-allreduce over ranks gives the mean.
+ *
+ * smc_cf_fused            RAW, or NORMALIZE on one GPU (internally: terminal pass, mean, payoff
+ *                          pass; terminals are staged in the workspace, contracts are
+ *                          processed in chunks that fit it).
+ * smc_fused_terminal      phase A of NORMALIZE for sharded runs: simulates and stores terminal
+ *                          prices (C, P_local) and their per-contract LOCAL sums (double[C]).
+ * smc_cf_from_terminal    phase B: payoff + CF from stored terminals, given the GLOBAL terminal
+ *                          sums (after the caller's allreduce) — or NULL for RAW.
+ */
+typedef struct smc_fused_args {
+  const double* contracts;   /* device, [n_contracts, 6]                                    */
+  int64_t n_contracts;
+  int64_t timesteps;
+  int64_t network_size;      /* N                                                            */
+  int64_t batches_total;     /* B of the whole job (all ranks)                               */
+  int64_t batch_begin;       /* local rows [batch_begin, batch_end)                          */
+  int64_t batch_end;
+  int dtype;
+  int scheme;
+  int normalization;
+  uint64_t seed;             /* SimulationParams.mc_seed (gbm.py:84)                         */
+  uint64_t first_matrix_index; /* SimulationParams.skip (gbm.py:86) at the first contract     */
+} smc_fused_args;
+
+size_t smc_cf_fused_workspace_bytes(const smc_fused_args* args);
+/* number of kernels one smc_cf_fused call launches for these arguments (for launch accounting) */
+int smc_cf_fused_launch_count(const smc_fused_args* args);
+int smc_cf_fused(const smc_fused_args* args, void* cf_out /* [n_contracts, N] complex */,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* args);
+int smc_fused_terminal(const smc_fused_args* args, void* terminal /* [n_contracts, P_local] */,
+                       double* terminal_sum /* device double[n_contracts] */, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+size_t smc_cf_from_terminal_workspace_bytes(const smc_fused_args* args);
+int smc_cf_from_terminal(const smc_fused_args* args, const void* terminal,
+                         const double* terminal_sum_global /* device double[C] or NULL */,
+                         void* cf_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer convenience for the reference-facing call: copies `contracts_host`
+ * (ideally pinned) to the device, runs smc_cf_fused, copies the [n_contracts, N] complex
+ * result to `cf_host` and synchronises `stream`.  args->contracts is ignored.  The workspace
+ * must be smc_cf_fused_host_workspace_bytes() (device memory). */
+size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* args);
+int smc_cf_fused_host(const smc_fused_args* args, const double* contracts_host, void* cf_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Pipe-peak calibration microbenchmarks (FP32 FMA issue and MUFU/XU), used by bench.py to
+ * state the compute roofline on the box it runs on: each runs `iters` dependent-chain
+ * iterations per thread on a full grid and returns executed lane-operations in *ops.
+ * kind: 0 = FFMA, 1 = MUFU.EX2, 2 = IMAD.WIDE.U32 + LOP3 (Philox-like mix). */
+int smc_pipe_calibrate(int kind, int64_t iters, double* ops, float* sink /* device, >= 1 */,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPECTRALMC_B200_H_ */

@@ -20,8 +20,8 @@ Stream definition
   block; (x0, x1) -> 52-bit radius uniform, (x2, x3) -> 52-bit angle uniform, one pair.
 * uniforms (exactly representable, open interval):
     f32: m = x >> 9;  u = (m + 0.5) * 2**-23, except the radius uniform when m == 0,
-         which is refined with the 9 discarded bits: u = ((x & 0x1ff) + 0.5) * 2**-32
-    f64: m = ((hi << 32) | lo) >> 12;  u = (m + 0.5) * 2**-52
+         which is refined with the 9 discarded low bits: u = ((x & 0x1ff) + 0.5) * 2**-32
+    f64: m = ((hi & 0xfffff) << 32) | lo;  u = (m + 0.5) * 2**-52
 * Box–Muller: r = sqrt(-2 ln u1), theta = 2 pi (u2 - 0.5); even row = r cos(theta),
   odd row = r sin(theta).
 
@@ -87,7 +87,7 @@ def uniform_f32_angle(x: np.ndarray) -> np.ndarray:
 
 
 def uniform_f64(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
-    m = ((hi.astype(np.uint64) << np.uint64(32)) | lo.astype(np.uint64)) >> np.uint64(12)
+    m = ((hi.astype(np.uint64) & np.uint64(0xFFFFF)) << np.uint64(32)) | lo.astype(np.uint64)
     return (m.astype(np.float64) + 0.5) * 2.0**-52
 
 

@@ -1,0 +1,329 @@
+"""ctypes binding of ``libspectralmc_b200.so`` (declared in ``include/spectralmc_b200.h``).
+
+This is the ONLY route from Python to the device kernels: there is no Numba, CuPy, Triton
+or CPU fallback on the path.  If the shared library is missing the import fails loudly.
+PyTorch is used purely as the owner of device memory and streams; the wrappers below pass
+raw pointers, sizes and the current ``cudaStream_t``.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libspectralmc_b200.so")
+
+SMC_F32, SMC_F64 = 0, 1
+SMC_LOG_EULER, SMC_SIMPLE_EULER, SMC_LOG_EULER_STEPWISE = 0, 1, 2
+SMC_NORMALIZE, SMC_RAW = 0, 1
+SMC_CF_MEAN_THEN_FFT, SMC_CF_ROW_FFT = 0, 1
+
+EXPORTS = (
+    "smc_version smc_last_error smc_device_info smc_philox_normals smc_gbm_paths_inplace "
+    "smc_gbm_terminal_from_normals smc_normalize_rows_workspace_bytes smc_normalize_rows smc_payoff "
+    "smc_means3_workspace_bytes smc_means3 smc_cf_fft_mean_workspace_bytes smc_cf_fft_mean "
+    "smc_cf_fused_workspace_bytes smc_cf_fused_launch_count smc_cf_fused smc_fused_terminal_workspace_bytes smc_fused_terminal "
+    "smc_cf_from_terminal_workspace_bytes smc_cf_from_terminal smc_cf_fused_host_workspace_bytes "
+    "smc_cf_fused_host smc_pipe_calibrate"
+).split()
+
+
+class SmcError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, code: int, message: str) -> None:
+        super().__init__(f"libspectralmc_b200 status {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class FusedArgs(Structure):
+    """``smc_fused_args`` (include/spectralmc_b200.h)."""
+
+    _fields_ = [
+        ("contracts", c_void_p),
+        ("n_contracts", c_int64),
+        ("timesteps", c_int64),
+        ("network_size", c_int64),
+        ("batches_total", c_int64),
+        ("batch_begin", c_int64),
+        ("batch_end", c_int64),
+        ("dtype", c_int),
+        ("scheme", c_int),
+        ("normalization", c_int),
+        ("seed", c_uint64),
+        ("first_matrix_index", c_uint64),
+    ]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(
+            f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C spectralmc_b200/csrc`). spectralmc_b200 has no fallback path."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.smc_version.restype = c_int
+    lib.smc_last_error.restype = c_char_p
+    for name in EXPORTS:
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        if name.endswith("_workspace_bytes"):
+            fn.restype = c_size_t
+    lib.smc_normalize_rows_workspace_bytes.argtypes = [c_int64, c_int64]
+    lib.smc_means3_workspace_bytes.argtypes = [c_int64]
+    lib.smc_cf_fft_mean_workspace_bytes.argtypes = [c_int64, c_int64, c_int]
+    for name in (
+        "smc_cf_fused_workspace_bytes",
+        "smc_fused_terminal_workspace_bytes",
+        "smc_cf_from_terminal_workspace_bytes",
+        "smc_cf_fused_host_workspace_bytes",
+    ):
+        getattr(lib, name).argtypes = [POINTER(FusedArgs)]
+    lib.smc_cf_fused_launch_count.argtypes = [POINTER(FusedArgs)]
+    lib.smc_cf_fused_launch_count.restype = c_int
+    lib.smc_device_info.argtypes = [POINTER(c_int)] * 3
+    lib.smc_philox_normals.argtypes = [c_void_p, c_int64, c_int64, c_int, c_uint64, c_uint64, c_void_p]
+    lib.smc_gbm_paths_inplace.argtypes = [c_void_p, c_int64, c_int64, c_int] + [c_double] * 5 + [c_int, c_int, c_void_p]
+    lib.smc_gbm_terminal_from_normals.argtypes = (
+        [c_void_p, c_int64, c_int64, c_int] + [c_double] * 5 + [c_int, c_void_p, c_void_p]
+    )
+    lib.smc_normalize_rows.argtypes = [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_payoff.argtypes = [c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]
+    lib.smc_means3.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_cf_fft_mean.argtypes = [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_cf_fused.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_fused_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_cf_from_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_cf_fused_host.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_pipe_calibrate.argtypes = [c_int, c_int64, POINTER(c_double), c_void_p, c_void_p]
+    return lib
+
+
+LIB = _load()
+LIB_PATH = _LIB_PATH
+
+
+def check(status: int) -> None:
+    if status != 0:
+        raise SmcError(status, LIB.smc_last_error().decode())
+
+
+def version() -> int:
+    return int(LIB.smc_version())
+
+
+def device_info() -> tuple[int, int, int]:
+    a, b, c = c_int(), c_int(), c_int()
+    check(LIB.smc_device_info(byref(a), byref(b), byref(c)))
+    return a.value, b.value, c.value
+
+
+# --------------------------------------------------------------------------- helpers
+def dtype_code(dtype: torch.dtype) -> int:
+    if dtype == torch.float32:
+        return SMC_F32
+    if dtype == torch.float64:
+        return SMC_F64
+    raise TypeError(f"unsupported dtype {dtype}")
+
+
+def complex_dtype(dtype: torch.dtype) -> torch.dtype:
+    return torch.complex64 if dtype == torch.float32 else torch.complex128
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (spectralmc_b200 has no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be C-contiguous")
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# --------------------------------------------------------------------------- wrappers
+def philox_normals(out: torch.Tensor, seed: int, matrix_index: int) -> torch.Tensor:
+    """K1: fill ``out`` (rows, cols) with the ``matrix_index``-th matrix of stream ``seed``."""
+    _require_cuda(out, "out")
+    rows, cols = out.shape
+    check(LIB.smc_philox_normals(out.data_ptr(), rows, cols, dtype_code(out.dtype), seed, matrix_index, _stream()))
+    return out
+
+
+def gbm_paths_inplace(
+    io: torch.Tensor, dt: float, X0: float, r: float, d: float, v: float, scheme: int, threads_per_block: int = 256
+) -> None:
+    """K2: the reference's ``SimulateBlackScholes`` launch on a materialised matrix."""
+    _require_cuda(io, "io")
+    rows, cols = io.shape
+    check(
+        LIB.smc_gbm_paths_inplace(
+            io.data_ptr(), rows, cols, dtype_code(io.dtype), dt, X0, r, d, v, scheme, threads_per_block, _stream()
+        )
+    )
+
+
+def gbm_terminal_from_normals(
+    normals: torch.Tensor, dt: float, X0: float, r: float, d: float, v: float, scheme: int
+) -> torch.Tensor:
+    _require_cuda(normals, "normals")
+    rows, cols = normals.shape
+    out = torch.empty(cols, dtype=normals.dtype, device=normals.device)
+    check(
+        LIB.smc_gbm_terminal_from_normals(
+            normals.data_ptr(), rows, cols, dtype_code(normals.dtype), dt, X0, r, d, v, scheme, out.data_ptr(), _stream()
+        )
+    )
+    return out
+
+
+def normalize_rows(sims: torch.Tensor, forwards: torch.Tensor) -> None:
+    _require_cuda(sims, "sims")
+    _require_cuda(forwards, "forwards")
+    rows, cols = sims.shape
+    if forwards.dtype != sims.dtype or forwards.numel() != rows:
+        raise ValueError("forwards must have one entry per row, in the dtype of sims")
+    ws = _workspace(LIB.smc_normalize_rows_workspace_bytes(rows, cols), sims.device)
+    check(
+        LIB.smc_normalize_rows(
+            sims.data_ptr(), rows, cols, dtype_code(sims.dtype), forwards.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
+        )
+    )
+
+
+def payoff(terminal: torch.Tensor, K: float, df: float) -> tuple[torch.Tensor, torch.Tensor]:
+    _require_cuda(terminal, "terminal")
+    put = torch.empty_like(terminal)
+    call = torch.empty_like(terminal)
+    check(
+        LIB.smc_payoff(
+            terminal.data_ptr(), terminal.numel(), dtype_code(terminal.dtype), K, df, put.data_ptr(), call.data_ptr(), _stream()
+        )
+    )
+    return put, call
+
+
+def means3(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor) -> torch.Tensor:
+    """Means of three equally long vectors -> device float64[3] (fixed-order reduction)."""
+    for t, n in ((a, "a"), (b, "b"), (c, "c")):
+        _require_cuda(t, n)
+    n = a.numel()
+    out = torch.empty(3, dtype=torch.float64, device=a.device)
+    ws = _workspace(LIB.smc_means3_workspace_bytes(n), a.device)
+    check(
+        LIB.smc_means3(
+            a.data_ptr(), b.data_ptr(), c.data_ptr(), n, dtype_code(a.dtype), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
+        )
+    )
+    return out
+
+
+def cf_fft_mean(mat: torch.Tensor, method: int = SMC_CF_MEAN_THEN_FFT) -> torch.Tensor:
+    """K7+K8: ``mean(fft(mat, axis=1), axis=0)`` of a (B, N) real matrix -> (N,) complex."""
+    _require_cuda(mat, "mat")
+    B, N = mat.shape
+    out = torch.empty(N, dtype=complex_dtype(mat.dtype), device=mat.device)
+    ws = _workspace(LIB.smc_cf_fft_mean_workspace_bytes(B, N, method), mat.device)
+    check(
+        LIB.smc_cf_fft_mean(
+            mat.data_ptr(), B, N, dtype_code(mat.dtype), method, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
+        )
+    )
+    return out
+
+
+def make_fused_args(
+    contracts: torch.Tensor | None,
+    n_contracts: int,
+    timesteps: int,
+    network_size: int,
+    batches_total: int,
+    dtype: torch.dtype,
+    scheme: int,
+    normalization: int,
+    seed: int,
+    first_matrix_index: int,
+    batch_begin: int = 0,
+    batch_end: int | None = None,
+) -> FusedArgs:
+    return FusedArgs(
+        contracts.data_ptr() if contracts is not None else None,
+        n_contracts,
+        timesteps,
+        network_size,
+        batches_total,
+        batch_begin,
+        batches_total if batch_end is None else batch_end,
+        dtype_code(dtype),
+        scheme,
+        normalization,
+        seed,
+        first_matrix_index,
+    )
+
+
+def cf_fused(args: FusedArgs, device: torch.device, dtype: torch.dtype, workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """The fused batch path: returns the (partial) CF targets ``[n_contracts, N]`` complex."""
+    out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=device)
+    need = LIB.smc_cf_fused_workspace_bytes(byref(args))
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, device)
+    check(LIB.smc_cf_fused(byref(args), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def fused_terminal(args: FusedArgs, device: torch.device, dtype: torch.dtype) -> tuple[torch.Tensor, torch.Tensor]:
+    paths_local = (args.batch_end - args.batch_begin) * args.network_size
+    terminal = torch.empty((args.n_contracts, paths_local), dtype=dtype, device=device)
+    tsum = torch.empty(args.n_contracts, dtype=torch.float64, device=device)
+    ws = _workspace(LIB.smc_fused_terminal_workspace_bytes(byref(args)), device)
+    check(LIB.smc_fused_terminal(byref(args), terminal.data_ptr(), tsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return terminal, tsum
+
+
+def cf_from_terminal(
+    args: FusedArgs, terminal: torch.Tensor, terminal_sum_global: torch.Tensor | None, dtype: torch.dtype
+) -> torch.Tensor:
+    _require_cuda(terminal, "terminal")
+    out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=terminal.device)
+    ws = _workspace(LIB.smc_cf_from_terminal_workspace_bytes(byref(args)), terminal.device)
+    tsum_ptr = terminal_sum_global.data_ptr() if terminal_sum_global is not None else None
+    check(
+        LIB.smc_cf_from_terminal(
+            byref(args), terminal.data_ptr(), tsum_ptr, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
+        )
+    )
+    return out
+
+
+def cf_fused_host(args: FusedArgs, contracts_host: torch.Tensor, out_host: torch.Tensor, workspace: torch.Tensor) -> None:
+    """Host-buffer entry point: H2D contracts, fused path, D2H targets, stream sync."""
+    check(
+        LIB.smc_cf_fused_host(
+            byref(args), contracts_host.data_ptr(), out_host.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()
+        )
+    )
+
+
+def cf_fused_host_workspace_bytes(args: FusedArgs) -> int:
+    return int(LIB.smc_cf_fused_host_workspace_bytes(byref(args)))
+
+
+def pipe_calibrate(kind: int, iters: int, device: torch.device) -> tuple[float, float]:
+    """Run one calibration kernel; returns (lane-ops executed, milliseconds)."""
+    sink = torch.zeros(4, dtype=torch.float32, device=device)
+    ops = c_double()
+    check(LIB.smc_pipe_calibrate(kind, max(iters // 16, 1), byref(ops), sink.data_ptr(), _stream()))  # warm-up
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    check(LIB.smc_pipe_calibrate(kind, iters, byref(ops), sink.data_ptr(), _stream()))
+    stop.record()
+    stop.synchronize()
+    return ops.value, start.elapsed_time(stop)

@@ -1,0 +1,758 @@
+// Fused batch path and CF estimate: in-register Philox normals -> GBM stepping -> payoff ->
+// column sums over batches -> one FFT per contract.
+//
+// Replaces, per training step, the reference's Python loop
+//   [ _simulate_fft(c) for c in sobol_inputs ] + cp.asarray(fft_values)
+//   (/root/reference/src/spectralmc/gbm_trainer.py:1546-1553, :806-817; gbm.py:400-488;
+//    async_normals.py:388-396)
+// and, for materialised inputs, cp.mean(cp.fft.fft(mat, axis=1), axis=0) (gbm_trainer.py:814-817).
+//
+// Structure (all reductions fixed-order, no float atomics => bit-reproducible):
+//   tile_kernel      one CTA per (contract, tile of batch rows).  Thread (r, col) owns column
+//                    `col` of the [B, N] payoff matrix and walks rows r, r+R, ... of its tile,
+//                    accumulating in float64; the CTA folds the R row-lanes in shared memory and
+//                    writes one partial column-sum vector per tile.
+//   reduce_tiles     folds the tile partials of a contract into <= 64 group vectors.
+//   cf_finalize      folds the groups, scales by 1/B and takes ONE length-N transform
+//                    (mean_b FFT_n(mat) == FFT_n(mean_b mat)) in float64 shared memory
+//                    (radix-2 for powers of two, table-driven DFT otherwise), then narrows to
+//                    the output complex width.
+// The tile size is a function of the problem shape only (never of the SM count), so results do
+// not depend on the device the job lands on.
+#include <algorithm>
+#include <cmath>
+
+#include "smc_device.cuh"
+#include "smc_internal.h"
+
+namespace smc {
+
+constexpr int CF_BLOCK = 256;
+constexpr int64_t TARGET_TILES = 16384;
+constexpr int MAX_GROUPS = 64;
+constexpr int SCHEME_LOG_STEPWISE = 2;  // SMC_LOG_EULER_STEPWISE
+
+enum Source { SRC_FUSED = 0, SRC_TERMINAL = 1, SRC_MATRIX = 2 };
+enum Output { OUT_COLSUM = 0, OUT_TERMINAL = 1 };
+
+struct TilePlan {
+  int chunk_w;          // columns covered per pass (min(N, 256))
+  int lanes_r;          // R: row lanes per pass (256 / chunk_w)
+  int64_t tile_rows;    // multiple of R
+  int64_t tiles;        // tiles per contract
+  int64_t groups;       // level-1 groups per contract (<= 64)
+  int64_t tiles_per_group;
+};
+
+static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n) {
+  TilePlan p;
+  p.chunk_w = static_cast<int>(std::min<int64_t>(n, CF_BLOCK));
+  p.lanes_r = CF_BLOCK / p.chunk_w;
+  const int64_t R = p.lanes_r;
+  int64_t want = (n_contracts * rows_local + TARGET_TILES - 1) / TARGET_TILES;
+  want = std::max<int64_t>(want, 1);
+  p.tile_rows = (want + R - 1) / R * R;
+  p.tile_rows = std::min<int64_t>(p.tile_rows, (rows_local + R - 1) / R * R);
+  p.tiles = (rows_local + p.tile_rows - 1) / p.tile_rows;
+  p.tiles_per_group = (p.tiles + MAX_GROUPS - 1) / MAX_GROUPS;
+  p.groups = (p.tiles + p.tiles_per_group - 1) / p.tiles_per_group;
+  return p;
+}
+
+struct TileParams {
+  const double* contracts;      // [*, 6], indexed by GLOBAL contract
+  int64_t contract0;            // first global contract handled by this launch
+  int64_t timesteps;
+  int64_t n;                    // network_size
+  int64_t batches_total;
+  int64_t row_begin, row_end;   // local batch rows
+  int64_t paths_local;          // (row_end - row_begin) * n
+  int64_t tile_rows, tiles;
+  int chunk_w, lanes_r;
+  int normalize;                // apply scale[c] = F / mean before the payoff
+  PhiloxKeys keys;
+  uint64_t first_matrix_index;
+  const void* terminal_in;      // [launch contracts, paths_local]   (SRC_TERMINAL)
+  const void* matrix;           // [rows, n]                         (SRC_MATRIX)
+  const double* terminal_sum;   // GLOBAL sums per launch contract   (normalize)
+  void* terminal_out;           // [launch contracts, paths_local]   (OUT_TERMINAL)
+  double* partial;              // [launch contracts, tiles, n]      (OUT_COLSUM)
+  double* term_partial;         // [launch contracts, tiles]         (OUT_TERMINAL)
+};
+
+// per-contract constants, derived in float64 and narrowed once
+template <typename Real>
+struct SimConsts {
+  Real X0, K, df, scale;
+  Real lin0, lin1;  // log-Euler: X_T = X0 * exp(lin0 + lin1 * sum z)   [log2 units for float32]
+                    // stepwise   : X *= exp(lin0 + lin1 z) per step
+                    // simple     : X = |X * (lin0 + lin1 z)|,  lin0 = 1 + (r - d) dt
+};
+
+template <typename Real, int SCHEME>
+__device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int64_t c_global,
+                                                       int64_t c_local) {
+  const ContractRow k = load_contract(p.contracts, c_global);
+  const double dt = k.T / static_cast<double>(p.timesteps);  // gbm.py:411
+  const double sdt = sqrt(dt);                               // gbm.py:243
+  const double unit = sizeof(Real) == 4 ? 1.4426950408889634074 : 1.0;  // float32 feeds MUFU.EX2
+  SimConsts<Real> s;
+  s.X0 = static_cast<Real>(k.X0);
+  s.K = static_cast<Real>(k.K);                  // gbm.py:467
+  s.df = static_cast<Real>(exp(-k.r * k.T));     // df[-1], gbm.py:431,466
+  if (SCHEME == SMC_LOG_EULER) {
+    const double drift_dt = (k.r - k.d - 0.5 * k.v * k.v) * dt;  // gbm.py:246,249
+    s.lin0 = static_cast<Real>(drift_dt * static_cast<double>(p.timesteps) * unit);
+    s.lin1 = static_cast<Real>(k.v * sdt * unit);
+  } else if (SCHEME == SCHEME_LOG_STEPWISE) {
+    s.lin0 = static_cast<Real>((k.r - k.d - 0.5 * k.v * k.v) * dt * unit);
+    s.lin1 = static_cast<Real>(k.v * sdt * unit);
+  } else {
+    s.lin0 = static_cast<Real>(1.0 + (k.r - k.d) * dt);  // gbm.py:252,255
+    s.lin1 = static_cast<Real>(k.v * sdt);
+  }
+  s.scale = Real(1);
+  if (p.normalize) {
+    // forwards[-1] / row_means[-1], gbm.py:430,437-438 (ratio formed in the engine dtype)
+    const Real fwd = static_cast<Real>(k.X0 * exp((k.r - k.d) * k.T));
+    const double paths_total = static_cast<double>(p.batches_total) * static_cast<double>(p.n);
+    const Real mean = static_cast<Real>(p.terminal_sum[c_local] / paths_total);
+    s.scale = fwd / mean;
+  }
+  return s;
+}
+
+template <typename Real, int SCHEME>
+__device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>& k) {
+  if (SCHEME == SMC_LOG_EULER) {
+    acc += z;
+  } else if (SCHEME == SCHEME_LOG_STEPWISE) {
+    if (sizeof(Real) == 4)
+      acc *= mufu_ex2(fmaf(static_cast<float>(k.lin1), static_cast<float>(z), static_cast<float>(k.lin0)));
+    else
+      acc *= exp(fma(static_cast<double>(k.lin1), static_cast<double>(z), static_cast<double>(k.lin0)));
+  } else {
+    const Real m = sizeof(Real) == 4 ? static_cast<Real>(fmaf(k.lin1, z, k.lin0))
+                                     : static_cast<Real>(fma(k.lin1, z, k.lin0));
+    acc = sizeof(Real) == 4 ? static_cast<Real>(fabsf(acc * m)) : static_cast<Real>(fabs(acc * m));
+  }
+}
+
+// terminal price of global path `col` of the matrix (k_lo, k_hi): every one of the `timesteps`
+// normals is drawn and consumed.
+template <int SCHEME>
+__device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
+                                                   const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
+  float acc = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
+  const uint32_t nq = static_cast<uint32_t>(timesteps >> 2);
+#pragma unroll 2
+  for (uint32_t q = 0; q < nq; ++q) {
+    float z[4];
+    normals4_f32(col, q, k_lo, k_hi, keys, z);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) consume<float, SCHEME>(acc, z[u], k);
+  }
+  const int rem = static_cast<int>(timesteps & 3);
+  if (rem) {
+    float z[4];
+    normals4_f32(col, nq, k_lo, k_hi, keys, z);
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (u < rem) consume<float, SCHEME>(acc, z[u], k);
+  }
+  if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
+  return acc;
+}
+
+template <int SCHEME>
+__device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, uint32_t col, int64_t timesteps,
+                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
+  double acc = SCHEME == SMC_LOG_EULER ? 0.0 : k.X0;
+  const uint32_t nq = static_cast<uint32_t>(timesteps >> 1);
+  for (uint32_t q = 0; q < nq; ++q) {
+    double z[2];
+    normals2_f64(col, q, k_lo, k_hi, keys, z);
+    consume<double, SCHEME>(acc, z[0], k);
+    consume<double, SCHEME>(acc, z[1], k);
+  }
+  if (timesteps & 1) {
+    double z[2];
+    normals2_f64(col, nq, k_lo, k_hi, keys, z);
+    consume<double, SCHEME>(acc, z[0], k);
+  }
+  if (SCHEME == SMC_LOG_EULER) return k.X0 * exp(fma(k.lin1, acc, k.lin0));
+  return acc;
+}
+
+template <typename Real, int SRC, int SCHEME, int OUT>
+__global__ void __launch_bounds__(CF_BLOCK) tile_kernel(const TileParams p) {
+  __shared__ double sm[CF_BLOCK];
+  const int64_t c_local = blockIdx.x / p.tiles;
+  const int64_t tile = blockIdx.x - c_local * p.tiles;
+  const int64_t c_global = p.contract0 + c_local;
+  const int64_t row0 = p.row_begin + tile * p.tile_rows;
+  const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
+
+  SimConsts<Real> k{};
+  if (SRC != SRC_MATRIX) k = make_consts<Real, SCHEME>(p, c_global, c_local);
+  const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
+  const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
+
+  const int r = threadIdx.x / p.chunk_w;
+  const int lc = threadIdx.x - r * p.chunk_w;
+  const int64_t local_base = c_local * p.paths_local - p.row_begin * p.n;  // + global path -> staging index
+  double tile_total = 0.0;
+
+  for (int64_t n0 = 0; n0 < p.n; n0 += p.chunk_w) {
+    const int64_t col = n0 + lc;
+    const bool active = (r < p.lanes_r) && (col < p.n);
+    double acc = 0.0;
+    if (active) {
+      for (int64_t row = row0 + r; row < row1; row += p.lanes_r) {
+        const int64_t path = row * p.n + col;  // global path index b*N + n (gbm_trainer.py:814-816)
+        Real val;
+        if (SRC == SRC_FUSED)
+          val = simulate_terminal<SCHEME>(k, static_cast<uint32_t>(path), p.timesteps, p.keys, k_lo, k_hi);
+        else if (SRC == SRC_TERMINAL)
+          val = __ldcs(static_cast<const Real*>(p.terminal_in) + local_base + path);
+        else
+          val = __ldcs(static_cast<const Real*>(p.matrix) + (path - p.row_begin * p.n));
+        if (OUT == OUT_TERMINAL) {
+          static_cast<Real*>(p.terminal_out)[local_base + path] = val;
+          acc += static_cast<double>(val);
+        } else if (SRC == SRC_MATRIX) {
+          acc += static_cast<double>(val);
+        } else {
+          if (p.normalize) val *= k.scale;                              // gbm.py:438
+          const Real diff = k.K - val;
+          const Real put = k.df * (diff > Real(0) ? diff : Real(0));    // gbm.py:473
+          acc += static_cast<double>(put);
+        }
+      }
+    }
+    if (OUT == OUT_COLSUM) {
+      sm[threadIdx.x] = acc;
+      __syncthreads();
+      if (r == 0 && col < p.n) {
+        double s = 0.0;
+        for (int rr = 0; rr < p.lanes_r; ++rr) s += sm[rr * p.chunk_w + lc];
+        p.partial[(c_local * p.tiles + tile) * p.n + col] = s;
+      }
+      __syncthreads();
+    } else {
+      tile_total += acc;
+    }
+  }
+  if (OUT == OUT_TERMINAL) {
+    const double t = block_sum(tile_total, sm);
+    if (threadIdx.x == 0) p.term_partial[c_local * p.tiles + tile] = t;
+  }
+}
+
+// level 1: groups of tile partials -> [contracts, groups, n]
+__global__ void __launch_bounds__(CF_BLOCK)
+    reduce_tiles_kernel(const double* __restrict__ partial, double* __restrict__ grouped, int64_t tiles,
+                        int64_t tiles_per_group, int64_t groups, int64_t n) {
+  const int64_t c = blockIdx.x / groups, g = blockIdx.x - c * groups;
+  const int64_t t0 = g * tiles_per_group, t1 = min(t0 + tiles_per_group, tiles);
+  const double* src = partial + c * tiles * n;
+  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+    double s = 0.0;
+    int64_t t = t0;
+    for (; t + 4 <= t1; t += 4) {
+      const double a = src[(t + 0) * n + col], b = src[(t + 1) * n + col];
+      const double cc = src[(t + 2) * n + col], d = src[(t + 3) * n + col];
+      s += a;
+      s += b;
+      s += cc;
+      s += d;
+    }
+    for (; t < t1; ++t) s += src[t * n + col];
+    grouped[(c * groups + g) * n + col] = s;
+  }
+}
+
+// sum of a contract's per-tile terminal sums (fixed order)
+__global__ void __launch_bounds__(CF_BLOCK)
+    terminal_sum_kernel(const double* __restrict__ term_partial, double* __restrict__ out, int64_t tiles) {
+  __shared__ double sm[32];
+  const int64_t c = blockIdx.x;
+  double s = 0.0;
+  for (int64_t t = threadIdx.x; t < tiles; t += CF_BLOCK) s += term_partial[c * tiles + t];
+  const double tot = block_sum(s, sm);
+  if (threadIdx.x == 0) out[c] = tot;
+}
+
+__device__ __forceinline__ unsigned bit_reverse(unsigned x, int bits) { return __brev(x) >> (32 - bits); }
+
+// One CTA per contract: fold `groups` vectors, scale, transform, narrow.
+// Shared memory (doubles): re[n], im[n], then the twiddle table (n/2 pairs for radix-2, n pairs for
+// the DFT).  mode: 0 radix-2 (n power of two), 1 table DFT, 2 DFT with on-the-fly twiddles and the
+// folded vector staged in `spill` (global) for n too large for shared memory.
+template <typename Real>
+__global__ void __launch_bounds__(CF_BLOCK)
+    cf_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
+                       int log2n, Real* __restrict__ out /* [contracts, n, 2] */, int64_t out_contract0,
+                       double* __restrict__ spill) {
+  extern __shared__ double smem[];
+  const int64_t c = blockIdx.x;
+  const double* src = vecs + c * groups * n;
+  Real* dst = out + (out_contract0 + c) * n * 2;
+  const double kTwoOverN = 2.0 / static_cast<double>(n);
+
+  if (mode == 2) {
+    double* x = spill + c * n;
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      double s = 0.0;
+      for (int64_t g = 0; g < groups; ++g) s += src[g * n + col];
+      x[col] = s * scale;
+    }
+    __syncthreads();  // x is written and read by this CTA only
+    for (int64_t kk = threadIdx.x; kk < n; kk += CF_BLOCK) {
+      double re = 0.0, im = 0.0;
+      int64_t m = 0;
+      for (int64_t j = 0; j < n; ++j) {
+        double sn, cs;
+        sincospi(-static_cast<double>(m) * kTwoOverN, &sn, &cs);
+        re = fma(x[j], cs, re);
+        im = fma(x[j], sn, im);
+        m += kk;
+        if (m >= n) m -= n;
+      }
+      dst[2 * kk] = static_cast<Real>(re);
+      dst[2 * kk + 1] = static_cast<Real>(im);
+    }
+    return;
+  }
+
+  double* re = smem;
+  double* im = smem + n;
+  double* twr = smem + 2 * n;
+  double* twi = twr + (mode == 0 ? n / 2 : n);
+  const int64_t ntw = mode == 0 ? n / 2 : n;
+  for (int64_t j = threadIdx.x; j < ntw; j += CF_BLOCK) {
+    double sn, cs;
+    sincospi(-static_cast<double>(j) * kTwoOverN, &sn, &cs);  // exp(-2 pi i j / n)
+    twr[j] = cs;
+    twi[j] = sn;
+  }
+  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+    double s = 0.0;
+    for (int64_t g = 0; g < groups; ++g) s += src[g * n + col];
+    int64_t where = col;
+    if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
+    re[where] = s * scale;
+    im[where] = 0.0;
+  }
+  __syncthreads();
+
+  if (mode == 0) {
+    for (int64_t half = 1; half < n; half <<= 1) {
+      const int64_t stride = n / (2 * half);
+      for (int64_t b = threadIdx.x; b < n / 2; b += CF_BLOCK) {
+        const int64_t j = b & (half - 1);
+        const int64_t i0 = ((b - j) << 1) + j, i1 = i0 + half;
+        const double wr = twr[j * stride], wi = twi[j * stride];
+        const double tr = wr * re[i1] - wi * im[i1];
+        const double ti = wr * im[i1] + wi * re[i1];
+        re[i1] = re[i0] - tr;
+        im[i1] = im[i0] - ti;
+        re[i0] += tr;
+        im[i0] += ti;
+      }
+      __syncthreads();
+    }
+    for (int64_t kk = threadIdx.x; kk < n; kk += CF_BLOCK) {
+      dst[2 * kk] = static_cast<Real>(re[kk]);
+      dst[2 * kk + 1] = static_cast<Real>(im[kk]);
+    }
+  } else {
+    for (int64_t kk = threadIdx.x; kk < n; kk += CF_BLOCK) {
+      double ar = 0.0, ai = 0.0;
+      int64_t m = 0;
+      for (int64_t j = 0; j < n; ++j) {
+        ar = fma(re[j], twr[m], ar);
+        ai = fma(re[j], twi[m], ai);
+        m += kk;
+        if (m >= n) m -= n;
+      }
+      dst[2 * kk] = static_cast<Real>(ar);
+      dst[2 * kk + 1] = static_cast<Real>(ai);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side orchestration
+// ------------------------------------------------------------------------------------------
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+
+struct FinalizePlan {
+  int mode, log2n;
+  size_t smem;
+};
+
+static FinalizePlan finalize_plan(int64_t n) {
+  FinalizePlan f{};
+  const bool pow2 = (n & (n - 1)) == 0;
+  f.log2n = 0;
+  while ((int64_t(1) << f.log2n) < n) ++f.log2n;
+  if (pow2 && static_cast<size_t>(n) * 24 <= SMEM_LIMIT) {
+    f.mode = 0;
+    f.smem = static_cast<size_t>(n) * 24;
+  } else if (static_cast<size_t>(n) * 32 <= SMEM_LIMIT) {
+    f.mode = 1;
+    f.smem = static_cast<size_t>(n) * 32;
+    f.log2n = 0;
+  } else {
+    f.mode = 2;
+    f.smem = 0;
+    f.log2n = 0;
+  }
+  if (f.mode == 0 && n == 1) f.smem = 32;
+  return f;
+}
+
+template <typename Real>
+static int launch_finalize(const double* vecs, int64_t contracts, int64_t groups, int64_t n, double scale,
+                           void* out, int64_t out_contract0, double* spill, cudaStream_t st) {
+  const FinalizePlan f = finalize_plan(n);
+  if (f.smem > 48 * 1024)
+    SMC_CUDA_OK(cudaFuncSetAttribute(cf_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(f.smem)));
+  cf_finalize_kernel<Real><<<static_cast<unsigned>(contracts), CF_BLOCK, f.smem, st>>>(
+      vecs, groups, n, scale, f.mode, f.log2n, static_cast<Real*>(out), out_contract0, spill);
+  SMC_LAUNCH_OK("cf_finalize_kernel");
+  return SMC_OK;
+}
+
+template <typename Real, int SRC, int OUT>
+static int launch_tile(const TileParams& p, int64_t contracts, int scheme, cudaStream_t st) {
+  const int64_t blocks = contracts * p.tiles;
+  if (blocks > 0x7fffffffLL) return set_error(SMC_EINVAL, "tile grid too large (%lld)", (long long)blocks);
+  const unsigned grid = static_cast<unsigned>(blocks);
+  if (SRC != SRC_FUSED || scheme == SMC_LOG_EULER)
+    tile_kernel<Real, SRC, SMC_LOG_EULER, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
+  else if (scheme == SMC_SIMPLE_EULER)
+    tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
+  else
+    tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
+  SMC_LAUNCH_OK("tile_kernel");
+  return SMC_OK;
+}
+
+// column partials -> (optional level 1) -> finalize
+template <typename Real>
+static int reduce_and_finalize(const TilePlan& plan, double* partial, double* grouped, int64_t contracts,
+                               int64_t n, double scale, void* out, int64_t out_contract0, double* spill,
+                               cudaStream_t st) {
+  const double* vecs = partial;
+  int64_t groups = plan.tiles;
+  if (plan.tiles > MAX_GROUPS) {
+    const unsigned grid = static_cast<unsigned>(plan.groups * contracts);
+    reduce_tiles_kernel<<<grid, CF_BLOCK, 0, st>>>(partial, grouped, plan.tiles, plan.tiles_per_group,
+                                                    plan.groups, n);
+    SMC_LAUNCH_OK("reduce_tiles_kernel");
+    vecs = grouped;
+    groups = plan.groups;
+  }
+  return launch_finalize<Real>(vecs, contracts, groups, n, scale, out, out_contract0, spill, st);
+}
+
+struct Workspace {
+  char* base;
+  size_t size, used;
+  template <typename T>
+  T* take(size_t count) {
+    const size_t bytes = align_up(count * sizeof(T));
+    T* p = reinterpret_cast<T*>(base + used);
+    used += bytes;
+    return p;
+  }
+};
+
+// bytes needed by the column-sum pipeline for `contracts` contracts
+static size_t colsum_bytes(const TilePlan& plan, int64_t contracts, int64_t n) {
+  size_t b = align_up(static_cast<size_t>(contracts) * plan.tiles * n * sizeof(double));
+  if (plan.tiles > MAX_GROUPS) b += align_up(static_cast<size_t>(contracts) * plan.groups * n * sizeof(double));
+  if (finalize_plan(n).mode == 2) b += align_up(static_cast<size_t>(contracts) * n * sizeof(double));
+  return b;
+}
+
+static int check_args(const char* fn, const smc_fused_args* a) {
+  SMC_REQUIRE(a != nullptr, "%s: args is NULL", fn);
+  SMC_REQUIRE(a->n_contracts > 0, "%s: n_contracts must be > 0", fn);
+  SMC_REQUIRE(a->timesteps > 0 && a->network_size > 0 && a->batches_total > 0,
+              "%s: timesteps, network_size and batches_total must be > 0", fn);
+  SMC_REQUIRE(a->batch_begin >= 0 && a->batch_begin < a->batch_end && a->batch_end <= a->batches_total,
+              "%s: invalid batch range [%lld, %lld) of %lld", fn, (long long)a->batch_begin,
+              (long long)a->batch_end, (long long)a->batches_total);
+  SMC_REQUIRE(a->dtype == SMC_F32 || a->dtype == SMC_F64, "%s: invalid dtype %d", fn, a->dtype);
+  SMC_REQUIRE(a->scheme >= 0 && a->scheme <= 2, "%s: invalid scheme %d", fn, a->scheme);
+  SMC_REQUIRE(a->normalization == SMC_NORMALIZE || a->normalization == SMC_RAW, "%s: invalid normalization %d",
+              fn, a->normalization);
+  SMC_REQUIRE(static_cast<double>(a->batches_total) * static_cast<double>(a->network_size) <= 4294967295.0,
+              "%s: total paths exceed the 32-bit path counter", fn);
+  SMC_REQUIRE(a->timesteps <= 0x7fffffffLL, "%s: timesteps too large", fn);
+  SMC_REQUIRE((a->first_matrix_index >> 62) == 0, "%s: first_matrix_index too large", fn);
+  return SMC_OK;
+}
+
+static TileParams base_params(const smc_fused_args* a, const TilePlan& plan) {
+  TileParams p{};
+  p.contracts = a->contracts;
+  p.timesteps = a->timesteps;
+  p.n = a->network_size;
+  p.batches_total = a->batches_total;
+  p.row_begin = a->batch_begin;
+  p.row_end = a->batch_end;
+  p.paths_local = (a->batch_end - a->batch_begin) * a->network_size;
+  p.tile_rows = plan.tile_rows;
+  p.tiles = plan.tiles;
+  p.chunk_w = plan.chunk_w;
+  p.lanes_r = plan.lanes_r;
+  p.keys = make_philox_keys(a->seed);
+  p.first_matrix_index = a->first_matrix_index;
+  return p;
+}
+
+// contracts per pass of the single-GPU NORMALIZE path, given the bytes left for staging
+static int64_t normalize_chunk(const smc_fused_args* a, const TilePlan& plan, size_t avail) {
+  const int64_t rows = a->batch_end - a->batch_begin;
+  const size_t per = align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
+                     colsum_bytes(plan, 1, a->network_size) + align_up(plan.tiles * sizeof(double)) + 512;
+  return static_cast<int64_t>(avail / per);
+}
+
+}  // namespace smc
+
+using namespace smc;
+
+extern "C" size_t smc_cf_fused_workspace_bytes(const smc_fused_args* a) {
+  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
+  const int64_t rows = a->batch_end - a->batch_begin;
+  const TilePlan plan = make_plan(a->n_contracts, rows, a->network_size);
+  if (a->normalization == SMC_RAW) return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
+  // NORMALIZE: stage terminals; cap the staging at 8 GiB by chunking contracts
+  const size_t per = align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
+                     colsum_bytes(plan, 1, a->network_size) + align_up(plan.tiles * sizeof(double)) + 512;
+  const size_t cap = size_t(8) << 30;
+  int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(a->n_contracts, static_cast<int64_t>(cap / per)));
+  return per * chunk + align_up(a->n_contracts * sizeof(double)) + 256;
+}
+
+extern "C" int smc_cf_fused_launch_count(const smc_fused_args* a) {
+  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
+  const int reduce = plan.tiles > MAX_GROUPS ? 1 : 0;
+  if (a->normalization == SMC_RAW) return 2 + reduce;  // tile + [reduce] + finalize
+  return 4 + reduce;  // terminal tile + terminal sum + payoff tile + [reduce] + finalize (per chunk)
+}
+
+template <typename Real>
+static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t rows = a->batch_end - a->batch_begin;
+  const int64_t n = a->network_size;
+  const TilePlan plan = make_plan(a->n_contracts, rows, n);
+  const double scale = 1.0 / static_cast<double>(a->batches_total);
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
+
+  if (a->normalization == SMC_RAW) {
+    if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
+      return set_error(SMC_EWORKSPACE, "smc_cf_fused: workspace %zu < %zu", ws_bytes,
+                       colsum_bytes(plan, a->n_contracts, n));
+    TileParams p = base_params(a, plan);
+    p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+    double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
+    double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
+    if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, st)) return e;
+    return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n, scale, cf_out, 0, spill, st);
+  }
+
+  // NORMALIZE on one device: needs the mean over ALL paths of a contract
+  if (a->batch_begin != 0 || a->batch_end != a->batches_total)
+    return set_error(SMC_EINVAL,
+                     "smc_cf_fused: NORMALIZE over a batch shard needs the global terminal mean; use "
+                     "smc_fused_terminal + allreduce + smc_cf_from_terminal");
+  double* term_sum = w.take<double>(a->n_contracts);
+  const size_t avail = ws_bytes > w.used ? ws_bytes - w.used : 0;
+  const int64_t chunk = std::min<int64_t>(a->n_contracts, normalize_chunk(a, plan, avail));
+  if (chunk < 1) return set_error(SMC_EWORKSPACE, "smc_cf_fused: workspace %zu too small for one contract", ws_bytes);
+  const size_t mark = w.used;
+  for (int64_t c0 = 0; c0 < a->n_contracts; c0 += chunk) {
+    const int64_t cc = std::min<int64_t>(chunk, a->n_contracts - c0);
+    w.used = mark;
+    TileParams p = base_params(a, plan);
+    p.contract0 = c0;
+    Real* staging = w.take<Real>(cc * p.paths_local);
+    p.term_partial = w.take<double>(cc * plan.tiles);
+    p.partial = w.take<double>(cc * plan.tiles * n);
+    double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(cc * plan.groups * n) : nullptr;
+    double* spill = finalize_plan(n).mode == 2 ? w.take<double>(cc * n) : nullptr;
+    p.terminal_out = staging;
+    if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, cc, a->scheme, st)) return e;
+    terminal_sum_kernel<<<static_cast<unsigned>(cc), CF_BLOCK, 0, st>>>(p.term_partial, term_sum + c0, plan.tiles);
+    SMC_LAUNCH_OK("terminal_sum_kernel");
+    p.terminal_in = staging;
+    p.terminal_out = nullptr;
+    p.terminal_sum = term_sum + c0;
+    p.normalize = 1;
+    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, cc, a->scheme, st)) return e;
+    if (int e = reduce_and_finalize<Real>(plan, p.partial, grouped, cc, n, scale, cf_out, c0, spill, st)) return e;
+  }
+  return SMC_OK;
+}
+
+extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, size_t ws_bytes, void* stream) {
+  clear_error();
+  if (int e = check_args("smc_cf_fused", a)) return e;
+  SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr, "smc_cf_fused: NULL pointer");
+  SMC_REQUIRE(ws != nullptr, "smc_cf_fused: workspace is NULL");
+  return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, cf_out, ws, ws_bytes, as_stream(stream))
+                             : cf_fused_impl<double>(a, cf_out, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- two-phase API for batch-sharded NORMALIZE -------------------------------------------
+extern "C" size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* a) {
+  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
+  return align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)) + 256;
+}
+
+template <typename Real>
+static int fused_terminal_impl(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
+                               size_t ws_bytes, cudaStream_t st) {
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
+  if (ws_bytes < align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)))
+    return set_error(SMC_EWORKSPACE, "smc_fused_terminal: workspace too small");
+  TileParams p = base_params(a, plan);
+  p.term_partial = static_cast<double*>(ws);
+  p.terminal_out = terminal;
+  if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, a->n_contracts, a->scheme, st)) return e;
+  terminal_sum_kernel<<<static_cast<unsigned>(a->n_contracts), CF_BLOCK, 0, st>>>(p.term_partial, terminal_sum,
+                                                                                  plan.tiles);
+  SMC_LAUNCH_OK("terminal_sum_kernel");
+  return SMC_OK;
+}
+
+extern "C" int smc_fused_terminal(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
+                                  size_t ws_bytes, void* stream) {
+  clear_error();
+  if (int e = check_args("smc_fused_terminal", a)) return e;
+  SMC_REQUIRE(a->contracts && terminal && terminal_sum && ws, "smc_fused_terminal: NULL pointer");
+  return a->dtype == SMC_F32 ? fused_terminal_impl<float>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream))
+                             : fused_terminal_impl<double>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream));
+}
+
+extern "C" size_t smc_cf_from_terminal_workspace_bytes(const smc_fused_args* a) {
+  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
+  return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
+}
+
+template <typename Real>
+static int cf_from_terminal_impl(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
+                                 void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = a->network_size;
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n);
+  if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
+    return set_error(SMC_EWORKSPACE, "smc_cf_from_terminal: workspace too small");
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
+  TileParams p = base_params(a, plan);
+  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
+  double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
+  p.terminal_in = terminal;
+  p.terminal_sum = tsum;
+  p.normalize = tsum != nullptr;
+  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, st)) return e;
+  return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n,
+                                   1.0 / static_cast<double>(a->batches_total), cf_out, 0, spill, st);
+}
+
+extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  clear_error();
+  if (int e = check_args("smc_cf_from_terminal", a)) return e;
+  SMC_REQUIRE(a->contracts && terminal && cf_out && ws, "smc_cf_from_terminal: NULL pointer");
+  SMC_REQUIRE((a->normalization == SMC_NORMALIZE) == (tsum != nullptr),
+              "smc_cf_from_terminal: terminal_sum_global must be given iff normalization is NORMALIZE");
+  return a->dtype == SMC_F32
+             ? cf_from_terminal_impl<float>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
+             : cf_from_terminal_impl<double>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- materialised payoff matrix -> CF -------------------------------------------------------
+extern "C" size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t n, int method) {
+  (void)method;
+  if (batches <= 0 || n <= 0) return 0;
+  return colsum_bytes(make_plan(1, batches, n), 1, n) + 256;
+}
+
+extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int dtype, int method, void* out,
+                               void* ws, size_t ws_bytes, void* stream) {
+  clear_error();
+  SMC_REQUIRE(mat && out && ws, "smc_cf_fft_mean: NULL pointer");
+  SMC_REQUIRE(batches > 0 && n > 0, "smc_cf_fft_mean: invalid shape (%lld, %lld)", (long long)batches, (long long)n);
+  SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_cf_fft_mean: invalid dtype %d", dtype);
+  SMC_REQUIRE(method == SMC_CF_MEAN_THEN_FFT || method == SMC_CF_ROW_FFT, "smc_cf_fft_mean: invalid method %d", method);
+  if (method == SMC_CF_ROW_FFT)
+    return set_error(SMC_EUNSUPPORTED, "smc_cf_fft_mean: SMC_CF_ROW_FFT is not built in this version");
+  const TilePlan plan = make_plan(1, batches, n);
+  if (ws_bytes < colsum_bytes(plan, 1, n)) return set_error(SMC_EWORKSPACE, "smc_cf_fft_mean: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
+  TileParams p{};
+  p.n = n;
+  p.batches_total = batches;
+  p.row_begin = 0;
+  p.row_end = batches;
+  p.paths_local = batches * n;
+  p.tile_rows = plan.tile_rows;
+  p.tiles = plan.tiles;
+  p.chunk_w = plan.chunk_w;
+  p.lanes_r = plan.lanes_r;
+  p.matrix = mat;
+  p.partial = w.take<double>(plan.tiles * n);
+  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(plan.groups * n) : nullptr;
+  double* spill = finalize_plan(n).mode == 2 ? w.take<double>(n) : nullptr;
+  const double scale = 1.0 / static_cast<double>(batches);
+  if (dtype == SMC_F32) {
+    if (int e = launch_tile<float, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, st)) return e;
+    return reduce_and_finalize<float>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
+  }
+  if (int e = launch_tile<double, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, st)) return e;
+  return reduce_and_finalize<double>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
+}
+
+// ---- host-buffer entry point ----------------------------------------------------------------
+extern "C" size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* a) {
+  if (a == nullptr || a->n_contracts <= 0) return 0;
+  const size_t cbytes = align_up(static_cast<size_t>(a->n_contracts) * 6 * sizeof(double));
+  const size_t obytes = align_up(static_cast<size_t>(a->n_contracts) * a->network_size * 2 * real_size(a->dtype));
+  return cbytes + obytes + smc_cf_fused_workspace_bytes(a);
+}
+
+extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contracts_host, void* cf_host, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  clear_error();
+  if (int e = check_args("smc_cf_fused_host", a)) return e;
+  SMC_REQUIRE(contracts_host && cf_host && ws, "smc_cf_fused_host: NULL pointer");
+  if (ws_bytes < smc_cf_fused_host_workspace_bytes(a))
+    return set_error(SMC_EWORKSPACE, "smc_cf_fused_host: workspace %zu < %zu", ws_bytes,
+                     smc_cf_fused_host_workspace_bytes(a));
+  cudaStream_t st = as_stream(stream);
+  const size_t cbytes = static_cast<size_t>(a->n_contracts) * 6 * sizeof(double);
+  const size_t obytes = static_cast<size_t>(a->n_contracts) * a->network_size * 2 * real_size(a->dtype);
+  char* base = static_cast<char*>(ws);
+  double* d_contracts = reinterpret_cast<double*>(base);
+  void* d_out = base + align_up(cbytes);
+  char* rest = base + align_up(cbytes) + align_up(obytes);
+  SMC_CUDA_OK(cudaMemcpyAsync(d_contracts, contracts_host, cbytes, cudaMemcpyHostToDevice, st));
+  smc_fused_args b = *a;
+  b.contracts = d_contracts;
+  if (int e = smc_cf_fused(&b, d_out, rest, ws_bytes - align_up(cbytes) - align_up(obytes), stream)) return e;
+  SMC_CUDA_OK(cudaMemcpyAsync(cf_host, d_out, obytes, cudaMemcpyDeviceToHost, st));
+  SMC_CUDA_OK(cudaStreamSynchronize(st));
+  return SMC_OK;
+}

@@ -1,0 +1,67 @@
+"""The C-ABI library loads and exports every symbol include/spectralmc_b200.h declares.
+No compute call is made here (there is no GPU on the CPU test box)."""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+from tests.conftest import ROOT
+
+
+def _declared() -> set[str]:
+    text = open(os.path.join(ROOT, "include", "spectralmc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(smc_[a-z0-9_]+)\s*\(", text))
+
+
+def test_library_exports_every_declared_symbol() -> None:
+    from spectralmc_b200 import _cabi
+
+    lib = ctypes.CDLL(_cabi.LIB_PATH)
+    declared = _declared()
+    assert len(declared) >= 20
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_cabi.EXPORTS), declared ^ set(_cabi.EXPORTS)
+
+
+def test_version_and_error_string() -> None:
+    from spectralmc_b200 import _cabi
+
+    assert _cabi.version() == 100
+    assert isinstance(_cabi.LIB.smc_last_error(), bytes)
+
+
+def test_workspace_queries_are_pure_host_functions() -> None:
+    from spectralmc_b200 import _cabi
+
+    assert _cabi.LIB.smc_means3_workspace_bytes(10_000) > 0
+    assert _cabi.LIB.smc_normalize_rows_workspace_bytes(12, 1024) > 0
+    assert _cabi.LIB.smc_cf_fft_mean_workspace_bytes(64, 16, 0) > 0
+    args = _cabi.make_fused_args(None, 4, 12, 16, 64, __import__("torch").float32, 0, 1, 42, 0)
+    raw = _cabi.LIB.smc_cf_fused_workspace_bytes(ctypes.byref(args))
+    args.normalization = 0
+    assert _cabi.LIB.smc_cf_fused_workspace_bytes(ctypes.byref(args)) > raw > 0
+
+
+def test_argument_validation_needs_no_device() -> None:
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    from spectralmc_b200 import _cabi
+
+    rc = _cabi.LIB.smc_philox_normals(None, 4, 4, 0, 1, 0, None)
+    assert rc == 1 and b"NULL" in _cabi.LIB.smc_last_error()
+    rc = _cabi.LIB.smc_gbm_paths_inplace(ctypes.c_void_p(16), 4, 4, 0, 0.1, 1.0, 0.0, 0.0, 0.2, 0, 48, None)
+    assert rc == 1 and b"threads_per_block" in _cabi.LIB.smc_last_error()
+    rc = _cabi.LIB.smc_payoff(ctypes.c_void_p(16), 4, 7, 1.0, 1.0, None, None, None)
+    assert rc == 1 and b"dtype" in _cabi.LIB.smc_last_error()
+
+
+def test_product_never_imports_the_oracle() -> None:
+    pkg = os.path.join(ROOT, "spectralmc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

@@ -1,0 +1,210 @@
+"""The fused batch path (smc_cf_fused and the two-phase NORMALIZE API) against the oracle run on
+the oracle's own statement of the same Philox normals, against analytic Black-76 (statistically,
+as the reference's tests/test_gbm.py:103-139 does against QuantLib), and against itself through
+size-independent properties (sharding, determinism, linearity).
+
+Tolerances: the fused float64 path sees the same normals as the oracle to ~1e-15, so CF vectors
+agree to 1e-12 norm-wise.  The fused float32 path draws its normals with MUFU (|dz| ~ 1e-6) and
+sums them in float32; against the float64-arithmetic oracle that is ~1e-6 norm-wise on the CF —
+the stated 1e-5 bound holds with margin for ordinary contracts and is asserted as such.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gbm as ogbm
+from oracle import philox
+from oracle.black76 import black76
+from oracle.sobol import sobol_contracts
+from spectralmc_b200 import _cabi
+from spectralmc_b200.effects import ForwardNormalization, PathScheme
+from spectralmc_b200.gbm import BlackScholes
+from spectralmc_b200.numerical import Precision
+from tests.helpers import expect_success, make_black_scholes_config, make_simulation_params, rel_max
+
+pytestmark = pytest.mark.gpu
+
+CANON = (100.0, 100.0, 1.0, 0.05, 0.0, 0.2)
+ODD = (37.5, 41.0, 2.5, -0.01, 0.03, 0.65)
+
+
+def _oracle_cf(rows, T, N, B, np_dtype, seed, first_index, scheme, norm):
+    out = []
+    for i, row in enumerate(rows):
+        z = philox.normals_matrix(T, N * B, np_dtype, seed, first_index + i)
+        cf, _ = ogbm.simulate_fft(ogbm.Contract(*row), z, N, scheme=scheme, normalization=norm)
+        out.append(np.asarray(cf, dtype=np.complex128))
+    return np.stack(out)
+
+
+def _fused(rows, T, N, B, dtype, seed, first_index, scheme, norm, **shard):
+    contracts = torch.tensor(np.asarray(rows, dtype=np.float64), device="cuda")
+    args = _cabi.make_fused_args(contracts, len(rows), T, N, B, dtype, scheme, norm, seed, first_index, **shard)
+    out = _cabi.cf_fused(args, contracts.device, dtype)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+CASES = [
+    # T, N, B  — c1 shape, ragged shapes, N > 256, T not a multiple of 4 / 2
+    (12, 16, 64), (1, 16, 32), (7, 12, 11), (5, 1, 40), (3, 300, 5), (252, 128, 16), (9, 64, 33), (2, 1024, 3),
+]
+
+
+@pytest.mark.parametrize("T,N,B", CASES)
+@pytest.mark.parametrize("scheme", ["log_euler", "simple_euler"])
+@pytest.mark.parametrize("norm", ["raw_paths", "normalize_forwards"])
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+def test_fused_matches_oracle(T, N, B, scheme, norm, prec) -> None:
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    rows = [CANON, ODD, (90.0, 100.0, 0.0, 0.03, 0.01, 0.3), (90.0, 100.0, 2.0, 0.03, 0.01, 0.0)]
+    ref = _oracle_cf(rows, T, N, B, np.dtype(prec), 42, 5, scheme, norm)
+    got = _fused(rows, T, N, B, dtype, 42, 5,
+                 _cabi.SMC_LOG_EULER if scheme == "log_euler" else _cabi.SMC_SIMPLE_EULER,
+                 _cabi.SMC_NORMALIZE if norm == "normalize_forwards" else _cabi.SMC_RAW)
+    tol = 1e-12 if prec == "float64" else 1e-5
+    for c in range(len(rows)):
+        assert rel_max(got[c], ref[c]) <= tol, (c, rel_max(got[c], ref[c]))
+    assert got.dtype == (np.complex128 if prec == "float64" else np.complex64)
+
+
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+def test_stepwise_exponential_variant_agrees(prec) -> None:
+    """prod_j exp(x_j) == exp(sum_j x_j): the per-step-exp kernel and the log-sum kernel agree."""
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    a = _fused([CANON, ODD], 50, 32, 64, dtype, 9, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    b = _fused([CANON, ODD], 50, 32, 64, dtype, 9, 0, _cabi.SMC_LOG_EULER_STEPWISE, _cabi.SMC_RAW)
+    assert rel_max(a, b) <= (1e-12 if prec == "float64" else 1e-5)
+
+
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+def test_fused_equals_materialised_pipeline(prec) -> None:
+    """Same counters => same normals: K1 -> K2 -> K6 -> K7/K8 on HBM equals the fused kernel."""
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    T, N, B = 37, 64, 128
+    fused = _fused([ODD], T, N, B, dtype, 77, 3, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)[0]
+    z = torch.empty((T, N * B), dtype=dtype, device="cuda")
+    _cabi.philox_normals(z, 77, 3)
+    X0, K, Tm, r, d, v = ODD
+    term = _cabi.gbm_terminal_from_normals(z, Tm / T, X0, r, d, v, _cabi.SMC_LOG_EULER)
+    put, _ = _cabi.payoff(term, K, math.exp(-r * Tm))
+    mat = _cabi.cf_fft_mean(put.view(B, N)).cpu().numpy()
+    assert rel_max(fused, mat) <= (1e-12 if prec == "float64" else 1e-5)
+
+
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+@pytest.mark.parametrize("norm", [_cabi.SMC_RAW, _cabi.SMC_NORMALIZE])
+def test_batch_sharding_sums_to_the_single_device_result(prec, norm) -> None:
+    """Ranks simulate disjoint batch rows with GLOBAL path counters; partial CFs add up
+    (SURVEY.md §8e).  NORMALIZE goes through the two-phase API with the summed terminal sums."""
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    T, N, B = 10, 32, 96
+    rows = [CANON, ODD, (5.0, 4.0, 0.7, 0.1, 0.0, 1.1)]
+    whole = _fused(rows, T, N, B, dtype, 11, 2, _cabi.SMC_LOG_EULER, norm)
+    contracts = torch.tensor(np.asarray(rows), device="cuda")
+    cuts = [0, 17, 64, 96]
+    shards = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        shards.append(_cabi.make_fused_args(contracts, len(rows), T, N, B, dtype, _cabi.SMC_LOG_EULER, norm, 11, 2,
+                                            batch_begin=lo, batch_end=hi))
+    if norm == _cabi.SMC_RAW:
+        total = sum(_cabi.cf_fused(a, contracts.device, dtype).cpu().numpy() for a in shards)
+    else:
+        staged = [_cabi.fused_terminal(a, contracts.device, dtype) for a in shards]
+        tsum = sum(s for _, s in staged)  # the allreduce
+        total = sum(_cabi.cf_from_terminal(a, t, tsum, dtype).cpu().numpy() for a, (t, _) in zip(shards, staged))
+        with pytest.raises(_cabi.SmcError, match="NORMALIZE"):
+            _cabi.cf_fused(shards[0], contracts.device, dtype)
+    assert rel_max(total, whole) <= (1e-13 if prec == "float64" else 2e-6)
+
+
+def test_bit_reproducible_and_skip_semantics() -> None:
+    """Fixed-order reductions: identical bits run to run; contract c of a batch starting at matrix k
+    equals a single-contract call at matrix k + c (each contract consumes one matrix, gbm.py:405)."""
+    rows = [CANON, ODD, CANON]
+    a = _fused(rows, 12, 16, 512, torch.float32, 42, 10, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    b = _fused(rows, 12, 16, 512, torch.float32, 42, 10, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    assert np.array_equal(a, b)
+    single = _fused([CANON], 12, 16, 512, torch.float32, 42, 12, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    assert np.array_equal(a[2], single[0])
+    assert not np.array_equal(a[0], a[2])  # same contract, different matrix
+
+
+def test_host_buffer_entry_point() -> None:
+    rows = torch.tensor([CANON, ODD], dtype=torch.float64).pin_memory()
+    args = _cabi.make_fused_args(None, 2, 12, 16, 64, torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 42, 0)
+    out = torch.empty((2, 16), dtype=torch.complex64).pin_memory()
+    ws = torch.empty(_cabi.cf_fused_host_workspace_bytes(args), dtype=torch.uint8, device="cuda")
+    _cabi.cf_fused_host(args, rows, out, ws)
+    dev = _fused([CANON, ODD], 12, 16, 64, torch.float32, 42, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    assert np.array_equal(out.numpy(), dev)
+
+
+def test_error_paths() -> None:
+    contracts = torch.tensor([CANON], dtype=torch.float64, device="cuda")
+    args = _cabi.make_fused_args(contracts, 1, 12, 16, 64, torch.float32, 0, 1, 42, 0)
+    out = torch.empty((1, 16), dtype=torch.complex64, device="cuda")
+    tiny = torch.empty(8, dtype=torch.uint8, device="cuda")
+    rc = _cabi.LIB.smc_cf_fused(_cabi.byref(args), out.data_ptr(), tiny.data_ptr(), 8, None)
+    assert rc == 3 and b"workspace" in _cabi.LIB.smc_last_error()
+    args.batch_end = 65
+    rc = _cabi.LIB.smc_cf_fused(_cabi.byref(args), out.data_ptr(), tiny.data_ptr(), 8, None)
+    assert rc == 1 and b"batch range" in _cabi.LIB.smc_last_error()
+    with pytest.raises(_cabi.SmcError, match="ROW_FFT"):
+        _cabi.cf_fft_mean(torch.zeros((4, 7), device="cuda"), _cabi.SMC_CF_ROW_FFT)
+
+
+# ---- statistical validation against analytic Black-Scholes ------------------------------------
+def _engine(precision, *, T=1, N=256, B=2**12, scheme=PathScheme.LOG_EULER, norm=ForwardNormalization.RAW, skip=0, seed=7):
+    sp = make_simulation_params(timesteps=T, network_size=N, batches_per_mc_run=B, threads_per_block=256,
+                                mc_seed=seed, buffer_size=1, skip=skip, dtype=precision)
+    return BlackScholes(make_black_scholes_config(sim_params=sp, path_scheme=scheme, normalization=norm))
+
+
+@pytest.mark.parametrize("precision", [Precision.float32, Precision.float64])
+@pytest.mark.parametrize("T", [1, 16])
+def test_fused_prices_match_black76(precision, T) -> None:
+    """64 Sobol contracts (seed 31) x 16 MC repetitions; DC bin / N is the put price.  Same
+    acceptance as the reference (tests/test_gbm.py:61-63,135-139): <= 5 % of contracts beyond 3
+    standard errors, RMSPE <= 0.15 where the analytic price is >= 1."""
+    rows = sobol_contracts(64, seed=31)
+    engine = _engine(precision, T=T)
+    N = 256
+    reps = []
+    for _ in range(16):
+        cf = expect_success(engine.cf_targets(torch.tensor(rows, device="cuda")))
+        reps.append(cf[:, 0].real.double().cpu().numpy() / N)
+    vals = np.stack(reps)  # [16, 64]
+    mean, sd = vals.mean(axis=0), vals.std(axis=0, ddof=1)
+    analytic = np.array([black76(*r)["put_price"] for r in rows])
+    se = sd / math.sqrt(vals.shape[0])
+    eps = 1e-4 if precision is Precision.float32 else 1e-8
+    z = np.where(se > 0, np.abs(mean - analytic) / np.where(se > 0, se, 1), np.where(np.abs(mean - analytic) <= eps * np.maximum(analytic, 1), 0.0, 4.0))
+    big = analytic >= 1.0
+    rmspe = float(np.sqrt(np.mean(((mean - analytic) / analytic)[big] ** 2)))
+    assert float(np.mean(z > 3.0)) <= 0.05, np.sort(z)[-5:]
+    assert rmspe <= 0.15
+    assert expect_success(engine.snapshot()).sim_params.skip == 16 * 64
+
+
+def test_full_size_headline_config_statistics() -> None:
+    """BASELINE config c2 at full size (fp32, T=252, N=128, B=65 536; 2.1e9 path-steps): the DC
+    bin prices the canonical put within 4 standard errors of Black-76; off-DC bins are sampling
+    noise of the predicted size; the imaginary DC part is exactly zero."""
+    engine = _engine(Precision.float32, T=252, N=128, B=65536, seed=7)
+    cf = expect_success(engine.simulate_fft(BlackScholes.Inputs(X0=100, K=100, T=1.0, r=0.05, d=0.0, v=0.2))).cpu().numpy()
+    ref = black76(*CANON)["put_price"]
+    put_sd = 7.2  # std of the discounted put payoff for this contract (analytic: ~7.2)
+    se = put_sd / math.sqrt(128 * 65536)
+    assert abs(cf[0].real / 128 - ref) <= 4 * se + 2e-5 * ref
+    assert cf[0].imag == 0.0
+    noise = put_sd * math.sqrt(128 / 65536)  # |CF_k| scale for k != 0
+    assert np.max(np.abs(cf[1:])) <= 6 * noise
+    assert np.sqrt(np.mean(np.abs(cf[1:]) ** 2)) > 0.3 * noise
+    # Hermitian symmetry of the DFT of a real vector
+    assert np.max(np.abs(cf[1:] - np.conj(cf[1:][::-1]))) <= 1e-5 * abs(cf[0])

@@ -1,0 +1,119 @@
+"""Host-side logic of the drop-in API (no device work): config validation, Result ADTs, the
+Sobol sampler — mirroring the reference's CPU-only assertions
+(tests/test_async_normals.py:153-170, tests/test_sobol_sampler.py:107-187)."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from spectralmc_b200.async_normals import BufferConfig, ConcurrentNormGeneratorConfig
+from spectralmc_b200.effects import ForwardNormalization, PathScheme
+from spectralmc_b200.errors import GPUMemoryLimitExceeded, InvalidSimulationParams
+from spectralmc_b200.gbm import BlackScholes, build_simulation_params
+from spectralmc_b200.numerical import Precision
+from spectralmc_b200.result import Failure, Success, collect_results, fold_results
+from spectralmc_b200.sobol_sampler import SobolConfig, SobolSampler, build_bound_spec, build_domain_bounds
+from tests.conftest import load_golden
+from tests.helpers import expect_failure, expect_success, make_black_scholes_config, make_domain_bounds, make_simulation_params
+
+
+def test_norm_config_validation() -> None:
+    bad_rows = ConcurrentNormGeneratorConfig.create(rows=0, cols=2, seed=1, dtype=Precision.float32, skips=0)
+    assert "InvalidShape" in str(expect_failure(bad_rows))
+    bad_seed = ConcurrentNormGeneratorConfig.create(rows=2, cols=2, seed=0, dtype=Precision.float32, skips=0)
+    assert "SeedOutOfRange" in str(expect_failure(bad_seed))
+    bad_skip = ConcurrentNormGeneratorConfig.create(rows=2, cols=2, seed=1, dtype=Precision.float32, skips=-1)
+    assert "SeedOutOfRange" in str(expect_failure(bad_skip))
+    assert isinstance(BufferConfig.create(0, 2, 2), Failure)
+    assert isinstance(BufferConfig.create(5, 2, 2), Failure)  # more buffers than elements
+    assert expect_success(BufferConfig.create(2, 2, 2)).size == 2
+
+
+def test_simulation_params_schema() -> None:
+    sp = make_simulation_params(timesteps=12, network_size=16, batches_per_mc_run=64, dtype=Precision.float64)
+    assert sp.total_paths() == 1024 and sp.total_blocks() == 4
+    with pytest.raises(Exception):
+        sp.timesteps = 3  # frozen
+    bad = build_simulation_params(timesteps=0, network_size=16, batches_per_mc_run=1, threads_per_block=256,
+                                  mc_seed=1, buffer_size=1, dtype=Precision.float32)
+    assert isinstance(expect_failure(bad), InvalidSimulationParams)
+    bad_tpb = build_simulation_params(timesteps=1, network_size=16, batches_per_mc_run=1, threads_per_block=48,
+                                      mc_seed=1, buffer_size=1, dtype=Precision.float32)
+    assert isinstance(expect_failure(bad_tpb), InvalidSimulationParams)
+    big = build_simulation_params(timesteps=1, network_size=1024, batches_per_mc_run=1_000_000, threads_per_block=256,
+                                  mc_seed=1, buffer_size=1, dtype=Precision.float32)
+    err = expect_failure(big)
+    assert isinstance(err, GPUMemoryLimitExceeded) and err.max_paths == 1_000_000_000
+    big64 = build_simulation_params(timesteps=1, network_size=1024, batches_per_mc_run=600_000, threads_per_block=256,
+                                    mc_seed=1, buffer_size=1, dtype=Precision.float64)
+    assert expect_failure(big64).max_paths == 500_000_000
+
+
+def test_config_defaults_and_inputs_validation() -> None:
+    cfg = make_black_scholes_config()
+    assert cfg.path_scheme is PathScheme.LOG_EULER and cfg.normalization is ForwardNormalization.NORMALIZE
+    assert list(BlackScholes.Inputs.model_fields) == ["X0", "K", "T", "r", "d", "v"]  # CVNN input order
+    BlackScholes.Inputs(X0=1.0, K=1.0, T=0.0, r=0.0, d=0.0, v=0.0)  # T = 0, v = 0 are legal
+    for bad in (dict(X0=0.0), dict(K=-1.0), dict(T=-0.1), dict(v=-0.1)):
+        with pytest.raises(Exception):
+            BlackScholes.Inputs(**{**dict(X0=1.0, K=1.0, T=1.0, r=0.0, d=0.0, v=0.1), **bad})
+
+
+def test_result_helpers() -> None:
+    assert collect_results([Success(1), Success(2)]) == Success([1, 2])
+    assert collect_results([Success(1), Failure("a"), Failure("b")]) == Failure("a")
+    assert fold_results([1, 2, 3], lambda acc, x: Success(acc + x), 0) == Success(6)
+    assert fold_results([1, -2, 3], lambda acc, x: Success(acc + x) if x > 0 else Failure("neg"), 0) == Failure("neg")
+    assert Success(2).map(lambda v: v + 1).unwrap() == 3 and Failure("e").unwrap_or(7) == 7
+    with pytest.raises(RuntimeError):
+        Failure("e").unwrap()
+
+
+# ---- Sobol -----------------------------------------------------------------------------------
+def _sampler(seed: int, skip: int = 0) -> SobolSampler:
+    return expect_success(SobolSampler.create(BlackScholes.Inputs, make_domain_bounds(), config=SobolConfig(seed=seed, skip=skip)))
+
+
+def test_sobol_contracts_bit_exact_with_reference() -> None:
+    """Golden rows came from the reference's own SobolSampler (make_golden.py)."""
+    g = load_golden("sobol_contracts")
+    for key, ref in g.items():
+        seed, skip, n = (int(t[len(p):]) for t, p in zip(key.split("_"), ("seed", "skip", "n")))
+        pts = expect_success(_sampler(seed, skip).sample(n))
+        got = np.array([[p.X0, p.K, p.T, p.r, p.d, p.v] for p in pts])
+        assert np.array_equal(got, ref), key
+        assert np.array_equal(expect_success(_sampler(seed, skip).sample_array(n)), ref), key
+
+
+def test_sobol_oracle_matches_golden() -> None:
+    from oracle.sobol import sobol_contracts
+
+    g = load_golden("sobol_contracts")
+    assert np.array_equal(sobol_contracts(16, 42), g["seed42_skip0_n16"])
+    assert np.array_equal(sobol_contracts(8, 42, skip=5), g["seed42_skip5_n8"])
+
+
+def test_sobol_skip_repro() -> None:
+    """skip = n is the same as burning n points (reference tests/test_sobol_sampler.py:131-150)."""
+    a = _sampler(42)
+    expect_success(a.sample(5))
+    rest = expect_success(a.sample(8))
+    skipped = expect_success(_sampler(42, skip=5).sample(8))
+    assert [tuple(p.model_dump().values()) for p in rest] == [tuple(p.model_dump().values()) for p in skipped]
+
+
+def test_sobol_bounds_and_validation() -> None:
+    pts = expect_success(_sampler(3).sample_array(256))
+    b = make_domain_bounds()
+    for i, f in enumerate(b.fields):
+        assert np.all(pts[:, i] >= b[f].lower - 1e-12) and np.all(pts[:, i] <= b[f].upper + 1e-12)
+    assert "NegativeSamples" in str(expect_failure(_sampler(3).sample(-1)))
+    assert expect_success(_sampler(3).sample(0)) == []
+    assert "BoundSpecInvalid" in str(expect_failure(build_bound_spec(1.0, 1.0)))
+    spec = {"X0": expect_success(build_bound_spec(0.0, 1.0))}
+    assert "DimensionMismatch" in str(expect_failure(build_domain_bounds(BlackScholes.Inputs, spec)))
+    # bounds that violate the model (X0 must be > 0) surface as SamplerValidationFailed
+    neg = expect_success(SobolSampler.create(BlackScholes.Inputs, make_domain_bounds(x0=(-5.0, -1.0)), config=SobolConfig(seed=1)))
+    assert "SamplerValidationFailed" in str(expect_failure(neg.sample(4)))
+    assert "SamplerValidationFailed" in str(expect_failure(neg.sample_array(4)))

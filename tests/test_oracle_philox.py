@@ -1,0 +1,99 @@
+"""The normal-stream specification (oracle/philox.py): Random123 known-answer vectors, an
+independent cross-check against NVIDIA's cuRAND Philox header compiled for the host, and the
+statistical quality of the Box–Muller output."""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import textwrap
+
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import philox
+
+# Random123 kat_vectors, philox4x32 with 10 rounds: (counter, key) -> output
+KAT = [
+    ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+    ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+    ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+     (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+]
+
+
+@pytest.mark.parametrize("ctr,key,expect", KAT)
+def test_random123_known_answers(ctr, key, expect) -> None:
+    out = philox.philox4x32_10(ctr, key)
+    assert tuple(int(x) for x in out) == expect
+
+
+@pytest.mark.skipif(shutil.which("nvcc") is None, reason="nvcc not on PATH")
+def test_against_curand_header_on_host(tmp_path) -> None:
+    """curand_philox4x32_x.h (CUDA toolkit) compiled as host code gives the same blocks."""
+    rng = np.random.default_rng(11)
+    ctrs = rng.integers(0, 2**32, size=(16, 4), dtype=np.uint64)
+    keys = rng.integers(0, 2**32, size=(16, 2), dtype=np.uint64)
+    rows = ",".join("{%s}" % ",".join(f"{int(v)}u" for v in list(c) + list(k)) for c, k in zip(ctrs, keys))
+    src = tmp_path / "kat.cu"
+    src.write_text(textwrap.dedent(f"""
+        #include <cstdio>
+        #include <cuda_runtime.h>
+        #define QUALIFIERS static inline __host__ __device__
+        #include <curand_philox4x32_x.h>
+        int main() {{
+          unsigned v[][6] = {{{rows}}};
+          for (auto& r : v) {{
+            uint4 c = {{r[0], r[1], r[2], r[3]}}; uint2 k = {{r[4], r[5]}};
+            uint4 o = curand_Philox4x32_10(c, k);
+            printf("%u %u %u %u\\n", o.x, o.y, o.z, o.w);
+          }}
+        }}"""))
+    exe = tmp_path / "kat"
+    subprocess.run(["nvcc", "-w", "-o", str(exe), str(src)], check=True, capture_output=True)
+    got = np.array([[int(t) for t in line.split()] for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n") if line])
+    for i in range(16):
+        out = philox.philox4x32_10(tuple(int(x) for x in ctrs[i]), tuple(int(x) for x in keys[i]))
+        assert [int(x) for x in out] == list(got[i])
+
+
+def test_uniforms_are_exact_and_open() -> None:
+    x = np.array([0, 1, 511, 512, 2**32 - 1, 0x80000000], dtype=np.uint32)
+    u = philox.uniform_f32_radius(x)
+    assert np.all((u > 0) & (u < 1))
+    assert np.all(u.astype(np.float32).astype(np.float64) == u)  # exactly representable in float32
+    assert u[0] == 0.5 * 2.0**-32 and u[2] == 511.5 * 2.0**-32 and u[3] == 1.5 * 2.0**-23
+    a = philox.uniform_f32_angle(x)
+    assert np.all((a > 0) & (a < 1)) and a[0] == 2.0**-24
+    hi = np.array([0, 0xFFFFFFFF], dtype=np.uint32)
+    d = philox.uniform_f64(hi, hi)
+    assert 0 < d[0] < d[1] < 1 and d[0] == 2.0**-53
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_normals_are_standard_normal(dtype) -> None:
+    z = philox.normals_matrix(64, 8192, dtype, seed=7, matrix_index=3).astype(np.float64).ravel()
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs(stats.skew(z)) < 5 * np.sqrt(6 / n)
+    assert abs(stats.kurtosis(z)) < 5 * np.sqrt(24 / n)
+    assert stats.kstest(z, "norm").pvalue > 1e-3
+    # rows (time steps) of one path are uncorrelated
+    zz = z.reshape(64, 8192)
+    c = np.corrcoef(zz[:8])
+    assert np.max(np.abs(c - np.eye(8))) < 6 / np.sqrt(8192)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_stream_is_a_pure_function_of_seed_index_row_col(dtype) -> None:
+    full = philox.normals_matrix(9, 40, dtype, seed=5, matrix_index=2)
+    part = philox.normals_matrix(9, 40, dtype, seed=5, matrix_index=2, col_begin=8, col_end=24)
+    assert np.array_equal(full[:, 8:24], part)
+    assert np.array_equal(full[:6], philox.normals_matrix(6, 40, dtype, seed=5, matrix_index=2)[:6]) or dtype == np.float64
+    assert not np.array_equal(full, philox.normals_matrix(9, 40, dtype, seed=5, matrix_index=3))
+    assert not np.array_equal(full, philox.normals_matrix(9, 40, dtype, seed=6, matrix_index=2))
+    other = np.float64 if dtype == np.float32 else np.float32
+    assert not np.allclose(full, philox.normals_matrix(9, 40, other, seed=5, matrix_index=2), atol=1e-3)
