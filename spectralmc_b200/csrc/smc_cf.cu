@@ -86,7 +86,7 @@ struct SimConsts {
   Real X0, K, df, scale;
   Real lin0, lin1;  // log-Euler: X_T = X0 * exp(lin0 + lin1 * sum z)   [log2 units for float32]
                     // stepwise   : X *= exp(lin0 + lin1 z) per step
-                    // simple     : X = |X * (lin0 + lin1 z)|,  lin0 = 1 + (r - d) dt
+                    // simple     : X = |X + X * (lin0 + lin1 z)|,  lin0 = (r - d) dt
 };
 
 template <typename Real, int SCHEME>
@@ -108,7 +108,9 @@ __device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int6
     s.lin0 = static_cast<Real>((k.r - k.d - 0.5 * k.v * k.v) * dt * unit);
     s.lin1 = static_cast<Real>(k.v * sdt * unit);
   } else {
-    s.lin0 = static_cast<Real>(1.0 + (k.r - k.d) * dt);  // gbm.py:252,255
+    // X += X * (lin0 + lin1 z): the increment is formed at full relative precision; folding the 1
+    // into lin0 would round (r - d) dt to an ulp of 1.0 and bias every step the same way.
+    s.lin0 = static_cast<Real>((k.r - k.d) * dt);  // gbm.py:252,255
     s.lin1 = static_cast<Real>(k.v * sdt);
   }
   s.scale = Real(1);
@@ -132,9 +134,14 @@ __device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>
     else
       acc *= exp(fma(static_cast<double>(k.lin1), static_cast<double>(z), static_cast<double>(k.lin0)));
   } else {
-    const Real m = sizeof(Real) == 4 ? static_cast<Real>(fmaf(k.lin1, z, k.lin0))
-                                     : static_cast<Real>(fma(k.lin1, z, k.lin0));
-    acc = sizeof(Real) == 4 ? static_cast<Real>(fabsf(acc * m)) : static_cast<Real>(fabs(acc * m));
+    if (sizeof(Real) == 4)
+      acc = static_cast<Real>(fabsf(fmaf(static_cast<float>(acc),
+                                         fmaf(static_cast<float>(k.lin1), static_cast<float>(z), static_cast<float>(k.lin0)),
+                                         static_cast<float>(acc))));
+    else
+      acc = static_cast<Real>(fabs(fma(static_cast<double>(acc),
+                                       fma(static_cast<double>(k.lin1), static_cast<double>(z), static_cast<double>(k.lin0)),
+                                       static_cast<double>(acc))));
   }
 }
 

@@ -15,7 +15,7 @@ constexpr int NORMALS_BLOCK = 256;
 constexpr int GROUPS_PER_THREAD = 4;  // row groups walked by one thread (16 rows f32 / 8 rows f64)
 
 template <int VEC>
-__global__ void __launch_bounds__(NORMALS_BLOCK)
+__global__ void __launch_bounds__(NORMALS_BLOCK, 4)
     philox_normals_f32_kernel(float* __restrict__ out, int64_t rows, int64_t cols, PhiloxKeys key,
                               uint32_t k_lo, uint32_t k_hi) {
   const int64_t col0 = (static_cast<int64_t>(blockIdx.x) * NORMALS_BLOCK + threadIdx.x) * VEC;

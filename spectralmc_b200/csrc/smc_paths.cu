@@ -75,8 +75,9 @@ struct Pack<double, 1> {
   using type = double;
 };
 
+// __launch_bounds__(1024): the CTA size is the caller's threads_per_block (32..1024, gbm.py:71)
 template <typename Real, int VEC, int SCHEME, bool STORE_PATHS>
-__global__ void gbm_paths_kernel(Real* __restrict__ io, const Real* __restrict__ normals,
+__global__ void __launch_bounds__(1024) gbm_paths_kernel(Real* __restrict__ io, const Real* __restrict__ normals,
                                  Real* __restrict__ terminal, int64_t rows, int64_t cols,
                                  PathConsts k) {
   using P = typename Pack<Real, VEC>::type;
