@@ -57,7 +57,7 @@ enum smc_normalization { SMC_NORMALIZE = 0, SMC_RAW = 1 };
 enum smc_cf_method {
   SMC_CF_MEAN_THEN_FFT = 0, /* FFT_n(mean_b mat): one length-N transform (linearity)          */
   SMC_CF_ROW_FFT = 1        /* mean_b FFT_n(mat[b,:]): a shared-memory/shuffle FFT per row,   */
-                            /* fused with the batch mean (N a power of two, 32 <= N <= 2048)  */
+                            /* fused with the batch mean (N a power of two, 32 <= N <= 512)   */
 };
 
 int smc_version(void);

@@ -69,6 +69,9 @@ struct TileParams {
   int64_t paths_local;          // (row_end - row_begin) * n
   int64_t tile_rows, tiles;
   int chunk_w, lanes_r;
+  int chunk_shift;              // log2(chunk_w) when it is a power of two, else -1
+  int64_t launch_contracts;     // contracts covered by this launch
+  const void* consts;           // SimConsts<Real>[launch contracts], written by prep_consts_kernel
   int normalize;                // apply scale[c] = F / mean before the payoff
   PhiloxKeys keys;
   uint64_t first_matrix_index;
@@ -89,8 +92,8 @@ struct SimConsts {
                     // simple     : X = |X + X * (lin0 + lin1 z)|,  lin0 = (r - d) dt
 };
 
-template <typename Real, int SCHEME>
-__device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int64_t c_global,
+template <typename Real>
+__device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int SCHEME, int64_t c_global,
                                                        int64_t c_local) {
   const ContractRow k = load_contract(p.contracts, c_global);
   const double dt = k.T / static_cast<double>(p.timesteps);  // gbm.py:411
@@ -122,6 +125,15 @@ __device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int6
     s.scale = fwd / mean;
   }
   return s;
+}
+
+// Per-contract constants are formed ONCE per launch sequence by this small kernel (float64
+// exp/sqrt/divide), so the hot kernel's CTAs start with a handful of loads instead of competing
+// for the FP64 and XU pipes in every prologue.
+template <typename Real>
+__global__ void __launch_bounds__(CF_BLOCK) prep_consts_kernel(const TileParams p, int scheme, SimConsts<Real>* out) {
+  const int64_t c_local = static_cast<int64_t>(blockIdx.x) * CF_BLOCK + threadIdx.x;
+  if (c_local < p.launch_contracts) out[c_local] = make_consts<Real>(p, scheme, p.contract0 + c_local, c_local);
 }
 
 template <typename Real, int SCHEME>
@@ -194,18 +206,23 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 template <typename Real, int SRC, int SCHEME, int OUT>
 __global__ void __launch_bounds__(CF_BLOCK) tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
-  const int64_t c_local = blockIdx.x / p.tiles;
-  const int64_t tile = blockIdx.x - c_local * p.tiles;
+  const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
+  if (c_local >= p.launch_contracts) return;
+  const int64_t tile = blockIdx.x;
   const int64_t c_global = p.contract0 + c_local;
   const int64_t row0 = p.row_begin + tile * p.tile_rows;
   const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
 
   SimConsts<Real> k{};
-  if (SRC != SRC_MATRIX) k = make_consts<Real, SCHEME>(p, c_global, c_local);
+  if (SRC != SRC_MATRIX) {
+    const Real* kc = reinterpret_cast<const Real*>(static_cast<const SimConsts<Real>*>(p.consts) + c_local);
+    k.X0 = __ldg(kc + 0); k.K = __ldg(kc + 1); k.df = __ldg(kc + 2); k.scale = __ldg(kc + 3);
+    k.lin0 = __ldg(kc + 4); k.lin1 = __ldg(kc + 5);
+  }
   const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
   const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
 
-  const int r = threadIdx.x / p.chunk_w;
+  const int r = p.chunk_shift >= 0 ? static_cast<int>(threadIdx.x >> p.chunk_shift) : static_cast<int>(threadIdx.x) / p.chunk_w;
   const int lc = threadIdx.x - r * p.chunk_w;
   const int64_t local_base = c_local * p.paths_local - p.row_begin * p.n;  // + global path -> staging index
   double tile_total = 0.0;
@@ -434,10 +451,17 @@ static int launch_finalize(const double* vecs, int64_t contracts, int64_t groups
 }
 
 template <typename Real, int SRC, int OUT>
-static int launch_tile(const TileParams& p, int64_t contracts, int scheme, cudaStream_t st) {
-  const int64_t blocks = contracts * p.tiles;
-  if (blocks > 0x7fffffffLL) return set_error(SMC_EINVAL, "tile grid too large (%lld)", (long long)blocks);
-  const unsigned grid = static_cast<unsigned>(blocks);
+static int launch_tile(TileParams p, int64_t contracts, int scheme, SimConsts<Real>* consts, cudaStream_t st) {
+  if (p.tiles > 0x7fffffffLL) return set_error(SMC_EINVAL, "tile grid too large (%lld)", (long long)p.tiles);
+  p.launch_contracts = contracts;
+  p.consts = consts;
+  p.chunk_shift = (p.chunk_w & (p.chunk_w - 1)) == 0 ? __builtin_ctz(static_cast<unsigned>(p.chunk_w)) : -1;
+  if (SRC != SRC_MATRIX) {
+    prep_consts_kernel<Real><<<static_cast<unsigned>((contracts + CF_BLOCK - 1) / CF_BLOCK), CF_BLOCK, 0, st>>>(p, scheme, consts);
+    SMC_LAUNCH_OK("prep_consts_kernel");
+  }
+  const dim3 grid(static_cast<unsigned>(p.tiles), static_cast<unsigned>(std::min<int64_t>(contracts, 65535)),
+                  static_cast<unsigned>((contracts + 65534) / 65535));
   if (SRC != SRC_FUSED || scheme == SMC_LOG_EULER)
     tile_kernel<Real, SRC, SMC_LOG_EULER, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
   else if (scheme == SMC_SIMPLE_EULER)
@@ -479,8 +503,11 @@ struct Workspace {
 };
 
 // bytes needed by the column-sum pipeline for `contracts` contracts
+constexpr size_t CONSTS_STRIDE = 64;  // >= sizeof(SimConsts<double>)
+
 static size_t colsum_bytes(const TilePlan& plan, int64_t contracts, int64_t n) {
   size_t b = align_up(static_cast<size_t>(contracts) * plan.tiles * n * sizeof(double));
+  b += align_up(static_cast<size_t>(contracts) * CONSTS_STRIDE);
   if (plan.tiles > MAX_GROUPS) b += align_up(static_cast<size_t>(contracts) * plan.groups * n * sizeof(double));
   if (finalize_plan(n).mode == 2) b += align_up(static_cast<size_t>(contracts) * n * sizeof(double));
   return b;
@@ -552,8 +579,8 @@ extern "C" int smc_cf_fused_launch_count(const smc_fused_args* a) {
   if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
   const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
   const int reduce = plan.tiles > MAX_GROUPS ? 1 : 0;
-  if (a->normalization == SMC_RAW) return 2 + reduce;  // tile + [reduce] + finalize
-  return 4 + reduce;  // terminal tile + terminal sum + payoff tile + [reduce] + finalize (per chunk)
+  if (a->normalization == SMC_RAW) return 3 + reduce;  // prep + tile + [reduce] + finalize
+  return 6 + reduce;  // (prep + terminal tile) + terminal sum + (prep + payoff tile) + [reduce] + finalize (per chunk)
 }
 
 template <typename Real>
@@ -570,9 +597,10 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
                        colsum_bytes(plan, a->n_contracts, n));
     TileParams p = base_params(a, plan);
     p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+    SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
     double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
     double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
-    if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, st)) return e;
+    if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
     return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n, scale, cf_out, 0, spill, st);
   }
 
@@ -594,17 +622,18 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
     Real* staging = w.take<Real>(cc * p.paths_local);
     p.term_partial = w.take<double>(cc * plan.tiles);
     p.partial = w.take<double>(cc * plan.tiles * n);
+    SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(cc * CONSTS_STRIDE));
     double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(cc * plan.groups * n) : nullptr;
     double* spill = finalize_plan(n).mode == 2 ? w.take<double>(cc * n) : nullptr;
     p.terminal_out = staging;
-    if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, cc, a->scheme, st)) return e;
+    if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, cc, a->scheme, consts, st)) return e;
     terminal_sum_kernel<<<static_cast<unsigned>(cc), CF_BLOCK, 0, st>>>(p.term_partial, term_sum + c0, plan.tiles);
     SMC_LAUNCH_OK("terminal_sum_kernel");
     p.terminal_in = staging;
     p.terminal_out = nullptr;
     p.terminal_sum = term_sum + c0;
     p.normalize = 1;
-    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, cc, a->scheme, st)) return e;
+    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, cc, a->scheme, consts, st)) return e;
     if (int e = reduce_and_finalize<Real>(plan, p.partial, grouped, cc, n, scale, cf_out, c0, spill, st)) return e;
   }
   return SMC_OK;
@@ -623,19 +652,22 @@ extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, siz
 extern "C" size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* a) {
   if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
   const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
-  return align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)) + 256;
+  return align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)) +
+         align_up(static_cast<size_t>(a->n_contracts) * CONSTS_STRIDE) + 256;
 }
 
 template <typename Real>
 static int fused_terminal_impl(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
                                size_t ws_bytes, cudaStream_t st) {
   const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
-  if (ws_bytes < align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)))
+  if (ws_bytes < smc_fused_terminal_workspace_bytes(a) - 256)
     return set_error(SMC_EWORKSPACE, "smc_fused_terminal: workspace too small");
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
   TileParams p = base_params(a, plan);
-  p.term_partial = static_cast<double*>(ws);
+  p.term_partial = w.take<double>(a->n_contracts * plan.tiles);
+  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
   p.terminal_out = terminal;
-  if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, a->n_contracts, a->scheme, st)) return e;
+  if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, a->n_contracts, a->scheme, consts, st)) return e;
   terminal_sum_kernel<<<static_cast<unsigned>(a->n_contracts), CF_BLOCK, 0, st>>>(p.term_partial, terminal_sum,
                                                                                   plan.tiles);
   SMC_LAUNCH_OK("terminal_sum_kernel");
@@ -667,12 +699,13 @@ static int cf_from_terminal_impl(const smc_fused_args* a, const void* terminal, 
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};
   TileParams p = base_params(a, plan);
   p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
   double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
   double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
   p.terminal_in = terminal;
   p.terminal_sum = tsum;
   p.normalize = tsum != nullptr;
-  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, st)) return e;
+  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
   return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n,
                                    1.0 / static_cast<double>(a->batches_total), cf_out, 0, spill, st);
 }
@@ -691,8 +724,8 @@ extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* termina
 
 // ---- materialised payoff matrix -> CF -------------------------------------------------------
 extern "C" size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t n, int method) {
-  (void)method;
   if (batches <= 0 || n <= 0) return 0;
+  if (method == SMC_CF_ROW_FFT && rowfft_supported(n)) return rowfft_workspace_bytes(batches, n);
   return colsum_bytes(make_plan(1, batches, n), 1, n) + 256;
 }
 
@@ -703,8 +736,7 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   SMC_REQUIRE(batches > 0 && n > 0, "smc_cf_fft_mean: invalid shape (%lld, %lld)", (long long)batches, (long long)n);
   SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_cf_fft_mean: invalid dtype %d", dtype);
   SMC_REQUIRE(method == SMC_CF_MEAN_THEN_FFT || method == SMC_CF_ROW_FFT, "smc_cf_fft_mean: invalid method %d", method);
-  if (method == SMC_CF_ROW_FFT)
-    return set_error(SMC_EUNSUPPORTED, "smc_cf_fft_mean: SMC_CF_ROW_FFT is not built in this version");
+  if (method == SMC_CF_ROW_FFT) return rowfft_mean(mat, batches, n, dtype, out, ws, ws_bytes, as_stream(stream));
   const TilePlan plan = make_plan(1, batches, n);
   if (ws_bytes < colsum_bytes(plan, 1, n)) return set_error(SMC_EWORKSPACE, "smc_cf_fft_mean: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -725,10 +757,10 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   double* spill = finalize_plan(n).mode == 2 ? w.take<double>(n) : nullptr;
   const double scale = 1.0 / static_cast<double>(batches);
   if (dtype == SMC_F32) {
-    if (int e = launch_tile<float, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, st)) return e;
+    if (int e = launch_tile<float, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, nullptr, st)) return e;
     return reduce_and_finalize<float>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
   }
-  if (int e = launch_tile<double, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, st)) return e;
+  if (int e = launch_tile<double, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, nullptr, st)) return e;
   return reduce_and_finalize<double>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
 }
 

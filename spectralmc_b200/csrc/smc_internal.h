@@ -24,6 +24,12 @@ inline size_t real_size(int dtype) { return dtype == SMC_F64 ? 8 : 4; }
 // number of SMs of the current device, cached
 int sm_count();
 
+// SMC_CF_ROW_FFT (smc_rowfft.cu)
+bool rowfft_supported(int64_t n);
+size_t rowfft_workspace_bytes(int64_t batches, int64_t n);
+int rowfft_mean(const void* mat, int64_t batches, int64_t n, int dtype, void* out, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+
 }  // namespace smc
 
 #define SMC_REQUIRE(cond, ...)                                   \

@@ -6,6 +6,9 @@
 // run of row groups; it evaluates one Philox block per (column, row group), transposes the
 // results in registers and issues one 16-byte store per row, so a warp writes 512 contiguous
 // bytes per row (coalesced, vectorised).
+#include <algorithm>
+#include <cstdlib>
+
 #include "smc_device.cuh"
 #include "smc_internal.h"
 
@@ -103,8 +106,10 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
   const uint32_t k_hi = static_cast<uint32_t>(matrix_index >> 32);
   cudaStream_t st = as_stream(stream);
   const bool aligned16 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+  const char* force_scalar = std::getenv("SMC_NORMALS_SCALAR");  // tuning knob
+  const bool allow_vec = !(force_scalar && force_scalar[0] == '1');
   if (dtype == SMC_F32) {
-    const bool vec = aligned16 && (cols % 4 == 0);
+    const bool vec = allow_vec && aligned16 && (cols % 4 == 0);
     const int v = vec ? 4 : 1;
     const int64_t nq = (rows + 3) / 4;
     dim3 grid(static_cast<unsigned>((cols / v + (cols % v != 0) + NORMALS_BLOCK - 1) / NORMALS_BLOCK),
@@ -114,7 +119,7 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
     else
       philox_normals_f32_kernel<1><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi);
   } else {
-    const bool vec = aligned16 && (cols % 2 == 0);
+    const bool vec = allow_vec && aligned16 && (cols % 2 == 0);
     const int v = vec ? 2 : 1;
     const int64_t nq = (rows + 1) / 2;
     dim3 grid(static_cast<unsigned>((cols / v + (cols % v != 0) + NORMALS_BLOCK - 1) / NORMALS_BLOCK),

@@ -1,0 +1,114 @@
+"""Multi-GPU sharding of the fused batch path: one process per GPU, batch rows partitioned across
+ranks, ONE sum-allreduce of the complex partial CF sums (plus one tiny allreduce of terminal-price
+sums in NORMALIZE mode, because the payoff is non-linear in the normalisation factor).
+
+The reference is single-GPU by policy (models/torch.py:160); this is new.  Every
+rank simulates ALL contracts over batch rows ``[begin, end)`` of the GLOBAL ``batches_per_mc_run``;
+Philox counters use the global path index, so the union over ranks is the single-GPU sample set and
+results are independent of the GPU count up to summation order.
+
+The device work goes through ``spectralmc_b200._cabi``; the collective is
+``torch.distributed.all_reduce`` (NCCL over NVLink on GPUs).  ``ops`` exists so the CPU test-suite
+can exercise the sharding/collective logic under ``gloo`` with a stand-in for the device calls.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Protocol
+
+import torch
+import torch.distributed as dist
+
+from spectralmc_b200 import _cabi
+from spectralmc_b200.effects import ForwardNormalization
+from spectralmc_b200.gbm import BlackScholes
+
+
+@dataclass(frozen=True)
+class BatchShard:
+    """Rows ``[begin, end)`` of the global batch dimension owned by ``rank``."""
+
+    rank: int
+    world_size: int
+    batches_total: int
+    begin: int
+    end: int
+
+    @property
+    def rows(self) -> int:
+        return self.end - self.begin
+
+
+def shard_batches(batches_total: int, world_size: int, rank: int) -> BatchShard:
+    """Contiguous, near-equal split in whole rows of ``network_size`` paths (FFT rows never split)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    if batches_total < world_size:
+        raise ValueError(f"cannot shard {batches_total} batch rows over {world_size} ranks")
+    base, extra = divmod(batches_total, world_size)
+    begin = rank * base + min(rank, extra)
+    return BatchShard(rank, world_size, batches_total, begin, begin + base + (1 if rank < extra else 0))
+
+
+class DeviceOps(Protocol):
+    def cf_fused(self, args: _cabi.FusedArgs) -> torch.Tensor: ...
+    def fused_terminal(self, args: _cabi.FusedArgs) -> tuple[torch.Tensor, torch.Tensor]: ...
+    def cf_from_terminal(self, args: _cabi.FusedArgs, terminal: torch.Tensor, tsum: torch.Tensor) -> torch.Tensor: ...
+
+
+class _CabiOps:
+    def __init__(self, device: torch.device, dtype: torch.dtype) -> None:
+        self.device, self.dtype = device, dtype
+
+    def cf_fused(self, args):
+        return _cabi.cf_fused(args, self.device, self.dtype)
+
+    def fused_terminal(self, args):
+        return _cabi.fused_terminal(args, self.device, self.dtype)
+
+    def cf_from_terminal(self, args, terminal, tsum):
+        return _cabi.cf_from_terminal(args, terminal, tsum, self.dtype)
+
+
+def _all_reduce_sum(t: torch.Tensor, group) -> None:
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
+
+
+def sharded_cf_targets(
+    engine: BlackScholes,
+    contracts: torch.Tensor,
+    *,
+    group=None,
+    ops: DeviceOps | None = None,
+    max_staging_bytes: int = 8 << 30,
+) -> torch.Tensor:
+    """CF targets ``[C, N]`` of ``contracts`` (``[C, 6]`` float64 on the engine's device), with the
+    batch dimension sharded over the ranks of ``group``.  Every rank returns the full result."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    sp = engine._sp
+    shard = shard_batches(sp.batches_per_mc_run, world, rank)
+    ops = ops or _CabiOps(engine._device, engine._dtype)
+    n = contracts.shape[0]
+    if engine._cfg.normalization is ForwardNormalization.RAW:
+        args = engine.fused_args(contracts, n, batch_begin=shard.begin, batch_end=shard.end)
+        out = ops.cf_fused(args)
+        _all_reduce_sum(out, group)
+        engine.consume(n)
+        return out
+    # NORMALIZE: stage terminals for a chunk of contracts, allreduce their sums, then the payoff pass
+    per_contract = shard.rows * sp.network_size * (4 if sp.dtype.value == "float32" else 8)
+    chunk = max(1, min(n, max_staging_bytes // max(per_contract, 1)))
+    outs = []
+    for c0 in range(0, n, chunk):
+        part = contracts[c0 : c0 + chunk].contiguous()
+        args = engine.fused_args(part, part.shape[0], batch_begin=shard.begin, batch_end=shard.end)
+        terminal, tsum = ops.fused_terminal(args)
+        _all_reduce_sum(tsum, group)
+        out = ops.cf_from_terminal(args, terminal, tsum)
+        _all_reduce_sum(out, group)
+        engine.consume(part.shape[0])
+        outs.append(out)
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

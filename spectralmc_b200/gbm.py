@@ -217,7 +217,9 @@ class BlackScholes:
         self._sp = cfg.sim_params
         self._dtype = self._sp.dtype.to_torch()
         self._np_dtype = self._sp.dtype.to_numpy()
-        self._device = torch.device("cuda", torch.cuda.current_device())
+        # resolved lazily enough that the host-side logic (argument packing, sharding, snapshots) can
+        # be exercised on a CPU-only box; any device operation there fails loudly in torch/_cabi
+        self._device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self._served = self._sp.skip  # matrices of the normal stream consumed so far
         ngen_cfg = ConcurrentNormGeneratorConfig.create(
             rows=self._sp.timesteps, cols=self._sp.total_paths(), seed=self._sp.mc_seed, dtype=self._sp.dtype, skips=self._sp.skip

@@ -155,8 +155,9 @@ def test_error_paths() -> None:
     args.batch_end = 65
     rc = _cabi.LIB.smc_cf_fused(_cabi.byref(args), out.data_ptr(), tiny.data_ptr(), 8, None)
     assert rc == 1 and b"batch range" in _cabi.LIB.smc_last_error()
-    with pytest.raises(_cabi.SmcError, match="ROW_FFT"):
-        _cabi.cf_fft_mean(torch.zeros((4, 7), device="cuda"), _cabi.SMC_CF_ROW_FFT)
+    with pytest.raises(_cabi.SmcError, match="ROW_FFT") as info:
+        _cabi.cf_fft_mean(torch.zeros((4, 7), device="cuda"), _cabi.SMC_CF_ROW_FFT)  # N not a power of two
+    assert info.value.code == 4
 
 
 # ---- statistical validation against analytic Black-Scholes ------------------------------------

@@ -131,6 +131,34 @@ def test_cf_fft_mean_shapes(dtype, b, n) -> None:
     assert rel_max(cf, ref) <= (2e-6 if dtype == torch.float32 else 1e-13)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("b,n", [(1, 32), (7, 32), (9, 64), (1000, 128), (65, 256), (33, 512), (4096, 128)])
+def test_cf_row_fft_method(dtype, b, n) -> None:
+    """SMC_CF_ROW_FFT: a register/shuffle FFT per row fused with the batch mean equals
+    numpy.mean(numpy.fft.fft(mat, axis=1), axis=0) and the mean-then-FFT method."""
+    rng = np.random.default_rng(b + n)
+    mat = (rng.random((b, n)) * 10).astype(np.float32 if dtype == torch.float32 else np.float64)
+    ref = np.mean(np.fft.fft(mat.astype(np.float64), axis=1), axis=0)
+    dev = torch.from_numpy(mat).cuda()
+    row = _cabi.cf_fft_mean(dev, _cabi.SMC_CF_ROW_FFT).cpu().numpy()
+    lin = _cabi.cf_fft_mean(dev, _cabi.SMC_CF_MEAN_THEN_FFT).cpu().numpy()
+    tol = 2e-6 if dtype == torch.float32 else 1e-13
+    assert rel_max(row, ref) <= tol and rel_max(row, lin) <= tol
+
+
+def test_cf_row_fft_on_reference_payoffs() -> None:
+    from tests.conftest import load_golden
+
+    g = load_golden("c1_float32_log_euler_raw_paths")  # N = 16 is below the method's range
+    with pytest.raises(_cabi.SmcError, match="ROW_FFT"):
+        _cabi.cf_fft_mean(torch.from_numpy(g["put_price"].copy()).cuda().view(64, 16), _cabi.SMC_CF_ROW_FFT)
+    # same payoffs viewed as 32 rows of 32: the estimate of THAT matrix
+    mat = g["put_price"].reshape(32, 32)
+    ref = np.mean(np.fft.fft(mat, axis=1), axis=0)
+    got = _cabi.cf_fft_mean(torch.from_numpy(mat.copy()).cuda(), _cabi.SMC_CF_ROW_FFT).cpu().numpy()
+    assert rel_max(got, ref) <= 2e-6
+
+
 def test_cf_large_network_size_fallback() -> None:
     mat = np.random.default_rng(0).random((2, 9000))
     cf = _cabi.cf_fft_mean(torch.from_numpy(mat).cuda()).cpu().numpy()

@@ -1,0 +1,159 @@
+// Tuning microbenchmark (not part of the product): times variants of the fused inner loop
+// (Philox4x32-10 -> Box-Muller -> log-return sum) to separate scheduling effects from pipe limits.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -I../../include -I../../spectralmc_b200/csrc \
+//        -o fused_variants fused_variants.cu && ./fused_variants
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "smc_device.cuh"
+
+using namespace smc;
+
+constexpr int T = 252;
+
+__device__ __forceinline__ uint32_t mulhi_ptx(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t mullo_ptx(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+template <int ROUNDS>
+__device__ __forceinline__ void philox_split(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& key,
+                                             uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint32_t h0 = mulhi_ptx(PHILOX_M0, c0), l0 = mullo_ptx(PHILOX_M0, c0);
+    const uint32_t h1 = mulhi_ptx(PHILOX_M1, c2), l1 = mullo_ptx(PHILOX_M1, c2);
+    const uint32_t n0 = h1 ^ c1 ^ key.k0[r];
+    const uint32_t n2 = h0 ^ c3 ^ key.k1[r];
+    c1 = l1; c3 = l0; c0 = n0; c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+template <int ROUNDS>
+__device__ __forceinline__ void philox_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& key,
+                                         uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < ROUNDS; ++r) {
+    const uint64_t p0 = static_cast<uint64_t>(PHILOX_M0) * c0;
+    const uint64_t p1 = static_cast<uint64_t>(PHILOX_M1) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ key.k0[r];
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ key.k1[r];
+    c1 = static_cast<uint32_t>(p1);
+    c3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c2 = n2;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// MODE 0 full; 1 no refinement branch; 2 philox only (xor-sum); 3 box-muller only (cheap counter hash)
+template <int ROUNDS, int MODE>
+__device__ __forceinline__ float block_sum4(uint32_t col, uint32_t q, const PhiloxKeys& key) {
+  uint32_t x[4];
+  if (MODE == 3) {
+    x[0] = col * 2654435761u + q * 40503u; x[1] = x[0] ^ (q * 2246822519u); x[2] = x[1] + col; x[3] = x[2] ^ 0x9e3779b9u;
+  } else if (MODE >= 4) {
+    philox_split<ROUNDS>(col, q, 7u, 0u, key, x);
+  } else {
+    philox_r<ROUNDS>(col, q, 7u, 0u, key, x);
+  }
+  if (MODE == 2 || MODE == 5) return __uint_as_float(((x[0] ^ x[1] ^ x[2] ^ x[3]) >> 9) | 0x3f800000u);
+  float ua = __uint_as_float((x[0] >> 9) + 0x3f800000u) - 0x1.fffffep-1f;
+  float uc = __uint_as_float((x[2] >> 9) + 0x3f800000u) - 0x1.fffffep-1f;
+  if (MODE == 0 || MODE == 4) {
+    if (__builtin_expect(min(x[0], x[2]) < 512u, 0)) {
+      ua = refine_radius_uniform(x[0], ua);
+      uc = refine_radius_uniform(x[2], uc);
+    }
+  }
+  float z0, z1, z2, z3;
+  box_muller_f32(ua, x[1], z0, z1);
+  box_muller_f32(uc, x[3], z2, z3);
+  return (z0 + z1) + (z2 + z3);
+}
+
+template <int ROUNDS, int MODE, int UNROLL, int PATHS, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) variant_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
+  const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * BLOCK;
+  float total = 0.f;
+  for (int64_t p = 0; p < paths_per_thread; p += PATHS) {
+    float s[PATHS];
+    uint32_t col[PATHS];
+#pragma unroll
+    for (int k = 0; k < PATHS; ++k) { s[k] = 0.f; col[k] = tid + static_cast<uint32_t>(p + k) * nthreads; }
+#pragma unroll UNROLL
+    for (uint32_t q = 0; q < T / 4; ++q) {
+#pragma unroll
+      for (int k = 0; k < PATHS; ++k) s[k] += block_sum4<ROUNDS, MODE>(col[k], q, key);
+    }
+#pragma unroll
+    for (int k = 0; k < PATHS; ++k) total += mufu_ex2(s[k] * 0.01f);
+  }
+  out[tid] = total;
+}
+
+template <int ROUNDS, int MODE, int UNROLL, int PATHS, int BLOCK, int MINB>
+void run(const char* name, int sms) {
+  const int64_t total_paths = 8388608;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant_kernel<ROUNDS, MODE, UNROLL, PATHS, BLOCK, MINB>, BLOCK, 0);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, variant_kernel<ROUNDS, MODE, UNROLL, PATHS, BLOCK, MINB>);
+  // same decomposition as the product: 16384 CTAs x 256 threads x 2 paths (scaled for other block sizes)
+  const int grid = static_cast<int>(total_paths / (2 * BLOCK) / (PATHS > 2 ? PATHS / 2 : 1));
+  const int64_t ppt = total_paths / (static_cast<int64_t>(grid) * BLOCK);
+  float* out;
+  cudaMalloc(&out, sizeof(float) * static_cast<size_t>(grid) * BLOCK);
+  const PhiloxKeys key = make_philox_keys(7);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a);
+    variant_kernel<ROUNDS, MODE, UNROLL, PATHS, BLOCK, MINB><<<grid, BLOCK>>>(out, ppt, key);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  const double steps = static_cast<double>(grid) * BLOCK * ppt * T;
+  printf("%-44s regs=%3d occ=%2d grid=%6d ppt=%3lld  %.3f ms  %.3e path-steps/s  %s\n", name, fa.numRegs, occ, grid,
+         (long long)ppt, best, steps / (best * 1e-3), e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(out);
+}
+
+int main() {
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  printf("SMs=%d\n", sms);
+  //   ROUNDS MODE UNROLL PATHS BLOCK MINB
+  run<10, 0, 2, 1, 256, 1>("base: unroll2 1path b256", sms);
+  run<10, 0, 1, 1, 256, 1>("unroll1", sms);
+  run<10, 0, 4, 1, 256, 1>("unroll4", sms);
+  run<10, 0, 2, 1, 256, 8>("unroll2 minb8 (<=32 regs)", sms);
+  run<10, 0, 1, 1, 256, 8>("unroll1 minb8", sms);
+  run<10, 0, 1, 2, 256, 1>("2 paths interleaved, unroll1", sms);
+  run<10, 0, 2, 2, 256, 1>("2 paths interleaved, unroll2", sms);
+  run<10, 0, 1, 4, 256, 1>("4 paths interleaved, unroll1", sms);
+  run<10, 0, 2, 1, 128, 1>("block128 unroll2", sms);
+  run<10, 0, 2, 1, 512, 1>("block512 unroll2", sms);
+  run<10, 1, 2, 1, 256, 1>("no refinement branch", sms);
+  run<10, 2, 2, 1, 256, 1>("philox only", sms);
+  run<10, 3, 2, 1, 256, 1>("box-muller only", sms);
+  run<10, 4, 2, 1, 256, 1>("split mul.hi/mul.lo full", sms);
+  run<10, 4, 1, 2, 256, 1>("split mul, 2 paths interleaved", sms);
+  run<10, 5, 2, 1, 256, 1>("split mul philox only", sms);
+  run<7, 0, 2, 1, 256, 1>("philox-7 full", sms);
+  run<7, 2, 2, 1, 256, 1>("philox-7 only", sms);
+  return 0;
+}
