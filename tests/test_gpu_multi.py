@@ -1,0 +1,63 @@
+"""Two real GPUs over NCCL: the sharded fused path (batch rows split across ranks, one
+all-reduce of the complex partial sums; NORMALIZE adds the terminal-sum all-reduce) reproduces the
+single-GPU result.  Skipped unless the box exposes >= 2 devices (run with `gpurun --gpus 2`)."""
+
+from __future__ import annotations
+
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROWS = [(100.0, 100.0, 1.0, 0.05, 0.0, 0.2), (37.5, 41.0, 2.5, -0.01, 0.03, 0.65), (5.0, 4.0, 0.7, 0.1, 0.0, 1.1)]
+
+
+def _worker(rank: int, world: int, port: int, prec: str, norm: str, queue) -> None:
+    import torch.distributed as dist
+
+    from spectralmc_b200.distributed import sharded_cf_targets
+    from spectralmc_b200.effects import ForwardNormalization, PathScheme
+    from spectralmc_b200.gbm import BlackScholes
+    from spectralmc_b200.numerical import Precision
+    from tests.helpers import expect_success, make_black_scholes_config, make_simulation_params
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        sp = make_simulation_params(timesteps=20, network_size=64, batches_per_mc_run=1001, mc_seed=5, skip=2, dtype=Precision(prec))
+        cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization(norm))
+        contracts = torch.tensor(ROWS, dtype=torch.float64, device="cuda")
+        sharded = sharded_cf_targets(BlackScholes(cfg), contracts)
+        whole = expect_success(BlackScholes(cfg).cf_targets(contracts))  # unsharded, on this rank alone
+        torch.cuda.synchronize()
+        queue.put((rank, sharded.cpu().numpy(), whole.cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+@pytest.mark.parametrize("norm", ["raw_paths", "normalize_forwards"])
+def test_two_gpu_sharding_matches_single_gpu(prec, norm) -> None:
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, prec, norm, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tol = 2e-6 if prec == "float32" else 1e-13
+    for rank, sharded, whole in results:
+        assert np.max(np.abs(sharded - whole)) <= tol * np.max(np.abs(whole)), rank
+    assert np.array_equal(results[0][1], results[1][1])
