@@ -94,9 +94,9 @@ using namespace smc;
 extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
                                   uint64_t matrix_index, void* stream) {
   clear_error();
-  SMC_REQUIRE(out != nullptr, "smc_philox_normals: out is NULL");
   SMC_REQUIRE(rows > 0 && cols > 0, "smc_philox_normals: invalid shape (%lld, %lld)", (long long)rows,
               (long long)cols);
+  SMC_REQUIRE(out != nullptr, "smc_philox_normals: out is NULL");
   SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_philox_normals: invalid dtype %d", dtype);
   SMC_REQUIRE(cols <= 0xffffffffLL, "smc_philox_normals: cols %lld exceeds the 32-bit path counter",
               (long long)cols);

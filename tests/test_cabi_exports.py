@@ -52,6 +52,8 @@ def test_argument_validation_needs_no_device() -> None:
 
     rc = _cabi.LIB.smc_philox_normals(None, 4, 4, 0, 1, 0, None)
     assert rc == 1 and b"NULL" in _cabi.LIB.smc_last_error()
+    rc = _cabi.LIB.smc_philox_normals(None, 0, 4, 0, 1, 0, None)
+    assert rc == 1 and b"shape" in _cabi.LIB.smc_last_error()
     rc = _cabi.LIB.smc_gbm_paths_inplace(ctypes.c_void_p(16), 4, 4, 0, 0.1, 1.0, 0.0, 0.0, 0.2, 0, 48, None)
     assert rc == 1 and b"threads_per_block" in _cabi.LIB.smc_last_error()
     rc = _cabi.LIB.smc_payoff(ctypes.c_void_p(16), 4, 7, 1.0, 1.0, None, None, None)
