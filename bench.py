@@ -69,7 +69,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -106,54 +106,41 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------
-def _cpu_worker(job):
+def cpu_pass(w: dict, sample_B: int, threads: int, matrix_index: int) -> float:
+    """One pass of the oracle's C restatement (oracle/gbm_oracle.c via oracle/cport.py) over
+    `sample_B` batch rows of the workload: Philox normals -> path stepping (float64 arithmetic, as
+    the reference kernel) -> payoff -> CF, on `threads` host threads.  Returns seconds."""
     import numpy as np
 
-    from oracle import gbm as ogbm
-    from oracle import philox
+    from oracle import cport
 
-    T, N, b_lo, b_hi, seed, k, dtype = job
-    z = philox.normals_matrix(T, N * (b_hi - b_lo), np.dtype(dtype), seed, k)  # this worker's own slice
-    c = ogbm.Contract(*CANON)
-    sr = ogbm.simulate(c, z, normalization=ogbm.RAW)
-    pr = ogbm.price(c, sr)
-    return np.fft.fft(pr.put_price.reshape(b_hi - b_lo, N), axis=1).sum(axis=0)
-
-
-def cpu_path(T: int, N: int, B: int, dtype: str, cores: int, pool) -> float:
-    """One pass of the oracle over B batch rows (normals + stepping + payoff + FFT/mean), split
-    over `cores` worker processes.  Returns seconds."""
-    import numpy as np
-
-    cuts = np.linspace(0, B, cores + 1).astype(int)
-    jobs = [(T, N, int(lo), int(hi), 7, i, dtype) for i, (lo, hi) in enumerate(zip(cuts[:-1], cuts[1:])) if hi > lo]
     t0 = time.perf_counter()
-    parts = pool.map(_cpu_worker, jobs)
-    _ = sum(parts) / B
+    cport.simulate_fft(CANON, w["T"], w["N"], sample_B, np.dtype(w["dtype"]), True, False, 7, matrix_index, threads=threads)
     return time.perf_counter() - t0
 
 
+def cpu_sample_rows(w: dict, args, cores: int) -> int:
+    # ~0.25-0.5 s of CPU work per pass at ~1e7 path-steps/s/core
+    return args.cpu_sample_batches or max(64, min(w["B"], int(cores * 4e6 / (w["T"] * w["N"]))))
+
+
 def run_reference(args) -> None:
-    """--impl reference: the reference's algorithm on the host cores (the reference itself is
-    GPU-only Python/Numba/CuPy and cannot run without CuPy) — the oracle port,
-    all cores, on a bounded sample of the same workload."""
+    """--impl reference: the reference's algorithm on the host cores.  The reference itself is
+    GPU-only Python (Numba + CuPy, import-time CUDA asserts) and cannot run on a CPU, so this arm
+    times the oracle port with every host thread on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
-
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
-    sample_B = args.cpu_sample_batches or max(cores * 8, 256)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        for _ in range(max(args.warmup, 1)):
-            cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
-        times = [cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool) for _ in range(args.steps)]
+    sample_B = cpu_sample_rows(w, args, cores)
+    for i in range(max(args.warmup, 1)):
+        cpu_pass(w, sample_B, cores, i)
+    times = [cpu_pass(w, sample_B, cores, 100 + i) for i in range(args.steps)]
     total = sum(times)
-    steps_done = args.steps * sample_B * w["N"] * w["T"]
-    value = steps_done / total
-    sample = f"{sample_B} of {w['B']} batch rows per step ({sample_B * w['N']} paths x {w['T']} steps), oracle NumPy port, fork pool"
+    value = args.steps * sample_B * w["N"] * w["T"] / total
+    sample = (f"each step = {sample_B} of {w['B']} batch rows ({sample_B * w['N']} paths x {w['T']} steps): normals + stepping + payoff + CF; "
+              f"oracle/gbm_oracle.c on {cores} threads")
     line = {
         "impl": "reference", "metric": "gbm_path_steps_per_sec", "value": value, "unit": "path-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -300,7 +287,10 @@ def run_b200(args) -> None:
             "bound": bound,
             "achieved": (issue_ach if bound == "fp32_issue" else xu_ach) / 1e12,
             "peak": (calib["ffma"] if bound == "fp32_issue" else calib["mufu"]) / 1e12,
-            "unit": "Tlane-op/s", "frac": max(fr_issue, fr_xu), "traffic": None,
+            "unit": "Tlane-op/s", "frac": max(fr_issue, fr_xu),
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` launch at this
+            # workload (profiles/r1_fused_f32_ncu_raw.csv): 22 528 B read, 0 B written; algorithmic input 48 B
+            "traffic": 22528 if args.workload == "c2" else None,
             "peak_source": "calibrated live: smc_pipe_calibrate (FFMA issue-rate and MUFU.EX2 microbenchmarks); MEASURED_PEAKS.json holds only HBM/bf16",
             "detail": {"issue_slots_per_path_step": ISSUE_SLOTS_PER_STEP, "xu_ops_per_path_step": XU_OPS_PER_STEP,
                        "fp32_issue": {"achieved": issue_ach / 1e12, "peak": calib["ffma"] / 1e12, "frac": fr_issue},
@@ -350,26 +340,23 @@ def materialised_roofline(_cabi, torch, dev, peaks, T, N, dtype) -> dict:
 
 
 def cpu_baseline(w: dict, args) -> dict:
-    import multiprocessing as mp
-
     cores = os.cpu_count() or 1
-    sample_B = args.cpu_sample_batches or max(cores * 8, 256)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
-        reps, total = 0, 0.0
-        while total < 10.0 and reps < 50:
-            total += cpu_path(w["T"], w["N"], sample_B, w["dtype"], cores, pool)
-            reps += 1
+    sample_B = cpu_sample_rows(w, args, cores) * 4
+    cpu_pass(w, sample_B, cores, 0)
+    reps, total = 0, 0.0
+    while total < 10.0 and reps < 40:
+        total += cpu_pass(w, sample_B, cores, 1 + reps)
+        reps += 1
     value = reps * sample_B * w["N"] * w["T"] / total
     return {"value": value, "unit": "path-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{reps} passes over {sample_B} of {w['B']} batch rows ({sample_B * w['N']} paths x {w['T']} steps each); oracle NumPy port over a {cores}-process fork pool"}
+            "sample": f"{reps} passes over {sample_B} of {w['B']} batch rows ({sample_B * w['N']} paths x {w['T']} steps each), {total:.1f} s; "
+                      f"oracle/gbm_oracle.c (plain C, float64 path arithmetic as the reference kernel) on {cores} threads"}
 
 
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

@@ -80,6 +80,81 @@ __device__ __forceinline__ float block_sum4(uint32_t col, uint32_t q, const Phil
   return (z0 + z1) + (z2 + z3);
 }
 
+// 21-bit uniforms: one Philox block -> 3 Box-Muller pairs -> 6 normals
+__device__ __forceinline__ float u21(uint32_t top_aligned) {  // field in bits 31..11
+  return __uint_as_float(((top_aligned >> 9) & 0x007ffffcu) | 0x3f800000u);
+}
+template <int MODE>
+__device__ __forceinline__ float block_sum6(uint32_t col, uint32_t q, const PhiloxKeys& key) {
+  uint32_t x[4];
+  philox_r<10>(col, q, 7u, 0u, key, x);
+  const uint32_t f0 = x[0], f1 = __funnelshift_l(x[1], x[0], 21), f2 = x[1] << 10;
+  const uint32_t f3 = x[2], f4 = __funnelshift_l(x[3], x[2], 21), f5 = x[3] << 10;
+  float ua = u21(f0) - 0x1.fffffcp-1f, ub = u21(f2) - 0x1.fffffcp-1f, uc = u21(f4) - 0x1.fffffcp-1f;
+  if (MODE == 0) {
+    if (__builtin_expect(min(min(f0, f2), f4) < 2048u, 0)) {
+      ua = refine_radius_uniform(x[0], ua); ub = refine_radius_uniform(x[1], ub); uc = refine_radius_uniform(x[2], uc);
+    }
+  }
+  float z0, z1, z2, z3, z4, z5;
+  {
+    const float w = u21(f1) - 1.5f; const float th = fmaf(w, 6.28318530717958648f, 1.4980281e-06f);
+    const float r = mufu_sqrt(-1.38629436111989062f * mufu_lg2(ua)); z0 = r * mufu_cos(th); z1 = r * mufu_sin(th);
+  }
+  {
+    const float w = u21(f3) - 1.5f; const float th = fmaf(w, 6.28318530717958648f, 1.4980281e-06f);
+    const float r = mufu_sqrt(-1.38629436111989062f * mufu_lg2(ub)); z2 = r * mufu_cos(th); z3 = r * mufu_sin(th);
+  }
+  {
+    const float w = u21(f5) - 1.5f; const float th = fmaf(w, 6.28318530717958648f, 1.4980281e-06f);
+    const float r = mufu_sqrt(-1.38629436111989062f * mufu_lg2(uc)); z4 = r * mufu_cos(th); z5 = r * mufu_sin(th);
+  }
+  return ((z0 + z1) + (z2 + z3)) + (z4 + z5);
+}
+
+template <int MODE, int UNROLL, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) variant6_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
+  const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * BLOCK;
+  float total = 0.f;
+  for (int64_t p = 0; p < paths_per_thread; ++p) {
+    float s = 0.f;
+    const uint32_t col = tid + static_cast<uint32_t>(p) * nthreads;
+#pragma unroll UNROLL
+    for (uint32_t q = 0; q < T / 6; ++q) s += block_sum6<MODE>(col, q, key);
+    total += mufu_ex2(s * 0.01f);
+  }
+  out[tid] = total;
+}
+
+template <int MODE, int UNROLL, int BLOCK, int MINB>
+void run6(const char* name) {
+  const int64_t total_paths = 8388608;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, variant6_kernel<MODE, UNROLL, BLOCK, MINB>, BLOCK, 0);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, variant6_kernel<MODE, UNROLL, BLOCK, MINB>);
+  const int grid = static_cast<int>(total_paths / (2 * BLOCK));
+  const int64_t ppt = 2;
+  float* out;
+  cudaMalloc(&out, sizeof(float) * static_cast<size_t>(grid) * BLOCK);
+  const PhiloxKeys key = make_philox_keys(7);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a);
+    variant6_kernel<MODE, UNROLL, BLOCK, MINB><<<grid, BLOCK>>>(out, ppt, key);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double steps = static_cast<double>(grid) * BLOCK * ppt * T;
+  printf("%-44s regs=%3d occ=%2d grid=%6d ppt=%3lld  %.3f ms  %.3e path-steps/s\n", name, fa.numRegs, occ, grid, (long long)ppt, best, steps / (best * 1e-3));
+  cudaFree(out);
+}
+
 template <int ROUNDS, int MODE, int UNROLL, int PATHS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) variant_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
   const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
@@ -150,9 +225,9 @@ int main() {
   run<10, 1, 2, 1, 256, 1>("no refinement branch", sms);
   run<10, 2, 2, 1, 256, 1>("philox only", sms);
   run<10, 3, 2, 1, 256, 1>("box-muller only", sms);
-  run<10, 4, 2, 1, 256, 1>("split mul.hi/mul.lo full", sms);
-  run<10, 4, 1, 2, 256, 1>("split mul, 2 paths interleaved", sms);
-  run<10, 5, 2, 1, 256, 1>("split mul philox only", sms);
+  run6<0, 1, 256, 1>("6 normals/block (21-bit), unroll1");
+  run6<0, 2, 256, 1>("6 normals/block (21-bit), unroll2");
+  run6<1, 2, 256, 1>("6 normals/block, no refinement");
   run<7, 0, 2, 1, 256, 1>("philox-7 full", sms);
   run<7, 2, 2, 1, 256, 1>("philox-7 only", sms);
   return 0;
