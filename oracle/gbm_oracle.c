@@ -38,11 +38,8 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-static double uniform_f32_radius(uint32_t x) {
-  const uint32_t m = x >> 9;
-  return m ? ((double)m + 0.5) * 0x1p-23 : ((double)(x & 0x1ffu) + 0.5) * 0x1p-32;
-}
-static double uniform_f32_angle(uint32_t x) { return ((double)(x >> 9) + 0.5) * 0x1p-23; }
+#define F32_REFINE_BIT 0x80000000u
+static double uniform_21(uint32_t field) { return ((double)field + 0.5) * 0x1p-21; }
 static double uniform_f64(uint32_t hi, uint32_t lo) {
   const uint64_t m = ((uint64_t)(hi & 0xfffffu) << 32) | lo;
   return ((double)m + 0.5) * 0x1p-52;
@@ -53,15 +50,26 @@ static void box_muller(double u1, double u2, double* even, double* odd) {
   *odd = r * sin(theta);
 }
 
-/* normals for rows [row0, row0 + nrows) x one column; nrows <= 4 (f32) / 2 (f64) per block */
-static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, uint64_t k, double z[4]) {
+/* one block of normals for column `col`, row group q: 6 values (float32 stream: 21-bit fields,
+ * three pairs, rare refinement block) or 2 values (float64 stream).  See oracle/philox.py. */
+static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, uint64_t k, double z[6]) {
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {col, q, (uint32_t)k, (uint32_t)(k >> 32) & 0x7fffffffu}, x[4];
   if (dtype == 0) {
     oracle_philox4x32_10(ctr, key, x);
-    box_muller(uniform_f32_radius(x[0]), uniform_f32_angle(x[1]), &z[0], &z[1]);
-    box_muller(uniform_f32_radius(x[2]), uniform_f32_angle(x[3]), &z[2], &z[3]);
-    for (int i = 0; i < 4; ++i) z[i] = (double)(float)z[i];
+    const uint32_t radius[3] = {x[0] >> 11, x[1] >> 11, x[2] >> 11};
+    const uint32_t angle[3] = {((x[0] & 0x7ffu) << 10) | (x[3] >> 22), ((x[1] & 0x7ffu) << 10) | ((x[3] >> 12) & 0x3ffu),
+                               ((x[2] & 0x7ffu) << 10) | ((x[3] >> 2) & 0x3ffu)};
+    uint32_t y[4] = {0, 0, 0, 0};
+    if (radius[0] == 0 || radius[1] == 0 || radius[2] == 0) {
+      uint32_t c2[4] = {col, q | F32_REFINE_BIT, ctr[2], ctr[3]};
+      oracle_philox4x32_10(c2, key, y);
+    }
+    for (int p = 0; p < 3; ++p) {
+      const double u1 = radius[p] ? uniform_21(radius[p]) : ((double)(y[p] >> 9) + 0.5) * 0x1p-44;
+      box_muller(u1, uniform_21(angle[p]), &z[2 * p], &z[2 * p + 1]);
+    }
+    for (int i = 0; i < 6; ++i) z[i] = (double)(float)z[i];
   } else {
     ctr[3] |= F64_STREAM_BIT;
     oracle_philox4x32_10(ctr, key, x);
@@ -71,11 +79,11 @@ static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, ui
 
 /* K1: the matrix_index-th (rows, cols) matrix; out is float (dtype 0) or double (dtype 1) */
 void oracle_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed, uint64_t matrix_index) {
-  const int per = dtype == 0 ? 4 : 2;
+  const int per = dtype == 0 ? 6 : 2;
   const int64_t nq = (rows + per - 1) / per;
   for (int64_t j = 0; j < cols; ++j) {
     for (int64_t q = 0; q < nq; ++q) {
-      double z[4];
+      double z[6];
       normals_block(dtype, (uint32_t)j, (uint32_t)q, seed, matrix_index, z);
       for (int i = 0; i < per && q * per + i < rows; ++i) {
         if (dtype == 0) ((float*)out)[(q * per + i) * cols + j] = (float)z[i];
@@ -111,12 +119,12 @@ double oracle_terminal_range(const double* contract, int64_t T, int dtype, int l
   const double X0 = contract[0], Tm = contract[2], r = contract[3], d = contract[4], v = contract[5];
   const double dt = Tm / (double)T, sqrt_dt = sqrt(dt); /* gbm.py:411,243 */
   const double drift = log_flag ? r - d - 0.5 * v * v : r - d;
-  const int per = dtype == 0 ? 4 : 2;
+  const int per = dtype == 0 ? 6 : 2;
   double tsum = 0.0;
   for (int64_t j = path_begin; j < path_end; ++j) {
     double X = X0;
     for (int64_t q = 0; q * per < T; ++q) {
-      double z[4];
+      double z[6];
       normals_block(dtype, (uint32_t)j, (uint32_t)q, seed, matrix_index, z);
       for (int i = 0; i < per && q * per + i < T; ++i) {
         const double dW = z[i] * sqrt_dt;

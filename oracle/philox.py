@@ -12,15 +12,20 @@ Stream definition
 (``k`` = the reference's ``skips`` counter, async_normals.py:394,400-408).
 
 * key      = (seed & 0xffffffff, seed >> 32)
-* float32: one Philox4x32-10 block per (column j, row-quad q = i // 4):
-  counter = (j, q, k & 0xffffffff, k >> 32); words (x0, x1) give rows 4q, 4q+1 and
-  (x2, x3) give rows 4q+2, 4q+3 through one Box–Muller pair each.
+* float32: one Philox4x32-10 block per (column j, row-group q = i // 6):
+  counter = (j, q, k & 0xffffffff, k >> 32); its 128 bits feed three Box–Muller pairs
+  (rows 6q+2p, 6q+2p+1 for pair p = 0, 1, 2) with 21-bit uniforms:
+    radius field  R_p = x_p >> 11
+    angle field   A_0 = (x0 & 0x7ff) << 10 | x3 >> 22
+                  A_1 = (x1 & 0x7ff) << 10 | (x3 >> 12) & 0x3ff
+                  A_2 = (x2 & 0x7ff) << 10 | (x3 >> 2) & 0x3ff
+  A zero radius field (probability 2**-21) is refined from word p of a SECOND block with
+  counter (j, q | 0x80000000, k lo, k hi): u = ((y_p >> 9) + 0.5) * 2**-44.
 * float64: one block per (column j, row-pair q = i // 2): counter as above with the
   top bit of word 3 set (``0x80000000 | k >> 32``) so the two precisions never share a
   block; (x0, x1) -> 52-bit radius uniform, (x2, x3) -> 52-bit angle uniform, one pair.
 * uniforms (exactly representable, open interval):
-    f32: m = x >> 9;  u = (m + 0.5) * 2**-23, except the radius uniform when m == 0,
-         which is refined with the 9 discarded low bits: u = ((x & 0x1ff) + 0.5) * 2**-32
+    f32: u = (F + 0.5) * 2**-21 for a 21-bit field F (radius: F = R_p unless R_p == 0, see above)
     f64: m = ((hi & 0xfffff) << 32) | lo;  u = (m + 0.5) * 2**-52
 * Box–Muller: r = sqrt(-2 ln u1), theta = 2 pi (u2 - 0.5); even row = r cos(theta),
   odd row = r sin(theta).
@@ -72,18 +77,28 @@ def _key(seed: int) -> tuple[int, int]:
     return seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
 
 
-def uniform_f32_radius(x: np.ndarray) -> np.ndarray:
-    """Radius uniform for float32 (float64 array holding exactly-representable f32 values)."""
-    x = x.astype(np.uint64)
-    m = x >> np.uint64(9)
-    coarse = (m.astype(np.float64) + 0.5) * 2.0**-23
-    fine = ((x & np.uint64(0x1FF)).astype(np.float64) + 0.5) * 2.0**-32
-    return np.where(m == 0, fine, coarse)
+F32_REFINE_BIT = 0x80000000
 
 
-def uniform_f32_angle(x: np.ndarray) -> np.ndarray:
-    m = x.astype(np.uint64) >> np.uint64(9)
-    return (m.astype(np.float64) + 0.5) * 2.0**-23
+def f32_fields(x0, x1, x2, x3):
+    """21-bit radius and angle fields of the three pairs of a float32 block."""
+    x0, x1, x2, x3 = (x.astype(np.uint64) for x in (x0, x1, x2, x3))
+    s = np.uint64
+    radius = [x0 >> s(11), x1 >> s(11), x2 >> s(11)]
+    angle = [
+        ((x0 & s(0x7FF)) << s(10)) | (x3 >> s(22)),
+        ((x1 & s(0x7FF)) << s(10)) | ((x3 >> s(12)) & s(0x3FF)),
+        ((x2 & s(0x7FF)) << s(10)) | ((x3 >> s(2)) & s(0x3FF)),
+    ]
+    return radius, angle
+
+
+def uniform_21(field: np.ndarray) -> np.ndarray:
+    return (field.astype(np.float64) + 0.5) * 2.0**-21
+
+
+def uniform_refined(y: np.ndarray) -> np.ndarray:
+    return ((y.astype(np.uint64) >> np.uint64(9)).astype(np.float64) + 0.5) * 2.0**-44
 
 
 def uniform_f64(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
@@ -121,13 +136,25 @@ def normals_matrix(
     k_lo, k_hi = matrix_index & 0xFFFFFFFF, (matrix_index >> 32) & 0x7FFFFFFF
     key = _key(seed)
     if dtype == np.float32:
-        nq = (rows + 3) // 4
+        nq = (rows + 5) // 6
         q = np.arange(nq, dtype=np.uint32)[:, None]
-        x0, x1, x2, x3 = philox4x32_10((j, q, k_lo, k_hi), key)
-        za, zb, ra = _box_muller(uniform_f32_radius(x0), uniform_f32_angle(x1))
-        zc, zd, rc = _box_muller(uniform_f32_radius(x2), uniform_f32_angle(x3))
-        z = np.stack([za, zb, zc, zd], axis=1).reshape(4 * nq, -1)[:rows]
-        rad = np.stack([ra, ra, rc, rc], axis=1).reshape(4 * nq, -1)[:rows]
+        x = philox4x32_10((j, q, k_lo, k_hi), key)
+        radius, angle = f32_fields(*x)
+        u1 = [uniform_21(r) for r in radius]
+        need = (radius[0] == 0) | (radius[1] == 0) | (radius[2] == 0)
+        if need.any():  # the rare refinement block
+            qq, jj = np.nonzero(need)
+            y = philox4x32_10((j[0, jj], q[qq, 0] | np.uint32(F32_REFINE_BIT), k_lo, k_hi), key)
+            for p in range(3):
+                hit = radius[p][qq, jj] == 0
+                u1[p][qq[hit], jj[hit]] = uniform_refined(y[p][hit])
+        zs, rs = [], []
+        for p in range(3):
+            ze, zo, r = _box_muller(u1[p], uniform_21(angle[p]))
+            zs += [ze, zo]
+            rs += [r, r]
+        z = np.stack(zs, axis=1).reshape(6 * nq, -1)[:rows]
+        rad = np.stack(rs, axis=1).reshape(6 * nq, -1)[:rows]
         z = z.astype(np.float32)
     elif dtype == np.float64:
         nq = (rows + 1) // 2

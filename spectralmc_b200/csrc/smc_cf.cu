@@ -163,20 +163,20 @@ template <int SCHEME>
 __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
   float acc = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
-  const uint32_t nq = static_cast<uint32_t>(timesteps >> 2);
-#pragma unroll 2
+  const uint32_t nq = static_cast<uint32_t>(timesteps / 6);
+#pragma unroll 1
   for (uint32_t q = 0; q < nq; ++q) {
-    float z[4];
-    normals4_f32(col, q, k_lo, k_hi, keys, z);
+    float z[6];
+    normals6_f32(col, q, k_lo, k_hi, keys, z);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) consume<float, SCHEME>(acc, z[u], k);
+    for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
   }
-  const int rem = static_cast<int>(timesteps & 3);
+  const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
   if (rem) {
-    float z[4];
-    normals4_f32(col, nq, k_lo, k_hi, keys, z);
+    float z[6];
+    normals6_f32(col, nq, k_lo, k_hi, keys, z);
 #pragma unroll
-    for (int u = 0; u < 3; ++u)
+    for (int u = 0; u < 5; ++u)
       if (u < rem) consume<float, SCHEME>(acc, z[u], k);
   }
   if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));

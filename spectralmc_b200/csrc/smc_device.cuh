@@ -85,43 +85,70 @@ __device__ __forceinline__ float mufu_ex2(float x) {
   return y;
 }
 
-// ---- float32 block: 4 words -> 2 Box–Muller pairs -> 4 normals ---------------------------
-// radius uniform u1 = (m + 0.5) 2^-23 with m = x >> 9 (one LEA.HI builds the float in [1, 2));
-// the m == 0 bin (probability 2^-23) is refined with the 9 low bits to (j + 0.5) 2^-32, so the
-// tail reaches 6.76 sigma.  Every step is exact in float32 and none is an integer->float
-// conversion (I2F would land on the XU pipe the MUFUs need).  The refinement sits behind a
-// single rarely-taken branch per block so the hot loop does not issue its instructions.
-static __device__ __noinline__ float refine_radius_uniform(uint32_t x, float u) {
-  if (x < 512u) {
-    const float t = __uint_as_float((x << 14) + 0x3f800000u);  // 1 + j 2^-9, j = x & 0x1ff
-    u = (t - 0x1.ff8p-1f) * 0x1p-23f;                          // (j + 0.5) 2^-9 * 2^-23
-  }
-  return u;
+// ---- float32 block: 4 words (128 bits) -> 3 Box–Muller pairs -> 6 normals ------------------
+// Each uniform gets 21 bits: the radius fields are the top 21 bits of x0, x1, x2; the angle
+// fields are the low 11 bits of the same word followed by a 10-bit slice of x3 (126 bits used).
+// u = (F + 0.5) 2^-21 is built as a float in [1, 2) with one shift/funnel-shift + one LOP3 and an
+// exact FADD — no integer->float conversion (I2F would land on the XU pipe the MUFUs need).
+// Six normals per block instead of four cuts the Philox (IMAD.WIDE) work per normal by a third;
+// the kernel is then bounded by the XU pipe and the issue port rather than by the FMA-heavy pipe.
+// A zero radius field (probability 2^-21) is refined with 23 fresh bits from a second block whose
+// counter has the top bit of the row-group word set, extending the tail to 7.9 sigma; it sits
+// behind one rarely-taken branch per block.
+constexpr uint32_t F32_REFINE_BIT = 0x80000000u;
+
+__device__ __forceinline__ float unit_float_21(uint32_t field_in_bits_22_2) {
+  return __uint_as_float((field_in_bits_22_2 & 0x007ffffcu) | 0x3f800000u);  // 1 + F 2^-21
 }
 
-__device__ __forceinline__ void box_muller_f32(float u1, uint32_t xb, float& z_even, float& z_odd) {
-  // w = u2 - 0.5 - 2^-24 exactly; theta = 2 pi (u2 - 0.5) in (-pi, pi)
-  const float w = __uint_as_float((xb >> 9) + 0x3f800000u) - 1.5f;
-  const float theta = fmaf(w, 6.28318530717958648f, 3.74507028e-07f /* 2 pi 2^-24 */);
+__device__ __forceinline__ void box_muller_f32(float u1, float angle_unit, float& z_even, float& z_odd) {
+  // angle_unit = 1 + A 2^-21;  u2 - 0.5 = (angle_unit - 1.5) + 2^-22;  theta = 2 pi (u2 - 0.5)
+  const float theta = fmaf(angle_unit - 1.5f, 6.28318530717958648f, 1.49802811e-06f /* 2 pi 2^-22 */);
   const float r = mufu_sqrt(-1.38629436111989062f /* -2 ln 2 */ * mufu_lg2(u1));
   z_even = r * mufu_cos(theta);
   z_odd = r * mufu_sin(theta);
 }
 
-// 4 normals for rows 4q .. 4q+3 of column `col` of matrix (k_lo, k_hi)
-__device__ __forceinline__ void normals4_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
-                                             const PhiloxKeys& key, float (&z)[4]) {
+// the rare path: radius field of pair `p` was zero -> u = (m + 0.5) 2^-44, m = top 23 bits of
+// word p of the refinement block.  Everything is passed by value (registers): taking the address
+// of the kernel-parameter key block would force a local-memory copy in the caller.
+static __device__ __noinline__ float3 refine_radius_uniforms(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                                             uint32_t seed_lo, uint32_t seed_hi, uint32_t x0, uint32_t x1,
+                                                             uint32_t x2, float u0, float u1, float u2) {
+  PhiloxKeys key;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    key.k0[r] = seed_lo + static_cast<uint32_t>(r) * PHILOX_W0;
+    key.k1[r] = seed_hi + static_cast<uint32_t>(r) * PHILOX_W1;
+  }
+  uint32_t y[4];
+  philox4x32_10(col, q | F32_REFINE_BIT, k_lo, k_hi, key, y);
+  if ((x0 >> 11) == 0u) u0 = (__uint_as_float((y[0] >> 9) + 0x3f800000u) - 0x1.fffffep-1f) * 0x1p-21f;
+  if ((x1 >> 11) == 0u) u1 = (__uint_as_float((y[1] >> 9) + 0x3f800000u) - 0x1.fffffep-1f) * 0x1p-21f;
+  if ((x2 >> 11) == 0u) u2 = (__uint_as_float((y[2] >> 9) + 0x3f800000u) - 0x1.fffffep-1f) * 0x1p-21f;
+  return make_float3(u0, u1, u2);
+}
+
+// 6 normals for rows 6q .. 6q+5 of column `col` of matrix (k_lo, k_hi)
+__device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                             const PhiloxKeys& key, float (&z)[6]) {
   uint32_t x[4];
   philox4x32_10(col, q, k_lo, k_hi, key, x);
-  // (1 + m 2^-23) - (1 - 2^-24) = (m + 0.5) 2^-23
-  float ua = __uint_as_float((x[0] >> 9) + 0x3f800000u) - 0x1.fffffep-1f;
-  float uc = __uint_as_float((x[2] >> 9) + 0x3f800000u) - 0x1.fffffep-1f;
-  if (__builtin_expect(min(x[0], x[2]) < 512u, 0)) {
-    ua = refine_radius_uniform(x[0], ua);
-    uc = refine_radius_uniform(x[2], uc);
+  float u[3];
+#pragma unroll
+  for (int p = 0; p < 3; ++p) u[p] = unit_float_21(x[p] >> 9) - 0x1.fffff8p-1f;  // (R + 0.5) 2^-21
+  if (__builtin_expect(min(min(x[0], x[1]), x[2]) < 2048u, 0)) {
+    const float3 f = refine_radius_uniforms(col, q, k_lo, k_hi, key.k0[0], key.k1[0], x[0], x[1], x[2], u[0], u[1], u[2]);
+    u[0] = f.x;
+    u[1] = f.y;
+    u[2] = f.z;
   }
-  box_muller_f32(ua, x[1], z[0], z[1]);
-  box_muller_f32(uc, x[3], z[2], z[3]);
+  const float a0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
+  const float a1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
+  const float a2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
+  box_muller_f32(u[0], a0, z[0], z[1]);
+  box_muller_f32(u[1], a1, z[2], z[3]);
+  box_muller_f32(u[2], a2, z[4], z[5]);
 }
 
 // ---- float64 block: 4 words -> 1 pair --------------------------------------------------

@@ -24,7 +24,7 @@ from tests.helpers import expect_success
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(12, 1024), (1, 16), (4, 4), (7, 132), (13, 1001), (5, 3), (252, 4096)]
+SHAPES = [(12, 1024), (1, 16), (4, 4), (6, 8), (7, 132), (13, 1001), (5, 3), (252, 4096)]
 
 
 def _device_matrix(rows, cols, dtype, seed, k):
@@ -61,6 +61,24 @@ def test_seed_and_index_select_the_matrix(dtype) -> None:
         assert np.max(np.abs(got - ref)) <= (1e-4 if dtype == torch.float32 else 1e-13)
     a, b = _device_matrix(6, 64, dtype, 9, 0), _device_matrix(6, 64, dtype, 9, 1)
     assert not np.allclose(a, b)
+
+
+def test_refined_tail_entries_match() -> None:
+    """Blocks whose 21-bit radius field is zero (probability 2^-21) take the radius from the
+    refinement block; locate them with the oracle and compare those entries explicitly."""
+    cols = 1 << 19
+    j = np.arange(cols, dtype=np.uint32)[None, :]
+    q = np.arange(4, dtype=np.uint32)[:, None]
+    radius, _ = philox.f32_fields(*philox.philox4x32_10((j, q, 0, 0), (7, 0)))
+    hits = [(int(a), int(b), p) for p in range(3) for a, b in zip(*np.nonzero(radius[p] == 0))]
+    assert hits
+    got = _device_matrix(24, cols, torch.float32, seed=7, k=0).astype(np.float64)
+    ref, rad = philox.normals_matrix(24, cols, np.float32, 7, 0, return_radius=True)
+    assert np.all(np.isfinite(got))
+    for qq, col, p in hits:
+        for row in (6 * qq + 2 * p, 6 * qq + 2 * p + 1):
+            assert rad[row, col] > 5.46
+            assert abs(got[row, col] - ref[row, col]) <= 2e-6 * (1 + abs(ref[row, col])) + 4e-7 / rad[row, col]
 
 
 def test_unaligned_output_takes_the_scalar_path() -> None:

@@ -60,16 +60,50 @@ def test_against_curand_header_on_host(tmp_path) -> None:
 
 
 def test_uniforms_are_exact_and_open() -> None:
-    x = np.array([0, 1, 511, 512, 2**32 - 1, 0x80000000], dtype=np.uint32)
-    u = philox.uniform_f32_radius(x)
-    assert np.all((u > 0) & (u < 1))
+    f = np.array([0, 1, 2**21 - 1], dtype=np.uint64)
+    u = philox.uniform_21(f)
+    assert np.all((u > 0) & (u < 1)) and u[0] == 2.0**-22 and u[2] == 1 - 2.0**-22
     assert np.all(u.astype(np.float32).astype(np.float64) == u)  # exactly representable in float32
-    assert u[0] == 0.5 * 2.0**-32 and u[2] == 511.5 * 2.0**-32 and u[3] == 1.5 * 2.0**-23
-    a = philox.uniform_f32_angle(x)
-    assert np.all((a > 0) & (a < 1)) and a[0] == 2.0**-24
+    y = np.array([0, 2**32 - 1], dtype=np.uint32)
+    r = philox.uniform_refined(y)
+    assert r[0] == 2.0**-45 and 0 < r[1] < 2.0**-21 and np.all(r.astype(np.float32).astype(np.float64) == r)
     hi = np.array([0, 0xFFFFFFFF], dtype=np.uint32)
     d = philox.uniform_f64(hi, hi)
     assert 0 < d[0] < d[1] < 1 and d[0] == 2.0**-53
+
+
+def test_float32_fields_partition_the_block() -> None:
+    """The six 21-bit fields use disjoint bits of the 128-bit block (126 used, 2 spare)."""
+    for bit in range(128):
+        words = [np.array([(1 << (bit - 32 * w)) if 32 * w <= bit < 32 * (w + 1) else 0], dtype=np.uint32) for w in range(4)]
+        radius, angle = philox.f32_fields(*words)
+        hits = sum(int(f[0] != 0) for f in radius + angle)
+        spare = bit in (96, 97)  # x3 bits 0 and 1
+        assert hits == (0 if spare else 1), bit
+    ones = [np.array([0xFFFFFFFF], dtype=np.uint32)] * 4
+    radius, angle = philox.f32_fields(*ones)
+    assert all(int(f[0]) == 2**21 - 1 for f in radius + angle)
+
+
+def test_refinement_block_is_used_for_zero_radius_fields() -> None:
+    """Columns whose radius field is zero take their radius from the refinement block: the value
+    is finite, beyond the 5.46-sigma cap of an unrefined 21-bit uniform is reachable, and the C
+    restatement agrees."""
+    from oracle import cport
+
+    cols = 1 << 19
+    j = np.arange(cols, dtype=np.uint32)[None, :]
+    q = np.arange(4, dtype=np.uint32)[:, None]
+    x = philox.philox4x32_10((j, q, 0, 0), (7, 0))
+    radius, _ = philox.f32_fields(*x)
+    hits = [(int(a), int(b), p) for p in range(3) for a, b in zip(*np.nonzero(radius[p] == 0))]
+    assert hits, "no zero radius field in 2M blocks?"
+    z, rad = philox.normals_matrix(24, cols, np.float32, 7, 0, return_radius=True)
+    c = cport.normals(24, cols, np.float32, 7, 0)
+    assert np.array_equal(z, c)
+    for qq, col, p in hits:
+        r = rad[6 * qq + 2 * p, col]
+        assert np.isfinite(r) and r > 5.46  # sqrt(-2 ln 2^-21.x) and beyond
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
