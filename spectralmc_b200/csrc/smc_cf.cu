@@ -29,6 +29,7 @@ namespace smc {
 
 constexpr int CF_BLOCK = 256;
 constexpr int64_t TARGET_TILES = 16384;
+constexpr int64_t STREAM_TILES = 2368;  // 16 x 148
 constexpr int MAX_GROUPS = 64;
 constexpr int SCHEME_LOG_STEPWISE = 2;  // SMC_LOG_EULER_STEPWISE
 
@@ -44,12 +45,17 @@ struct TilePlan {
   int64_t tiles_per_group;
 };
 
-static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n) {
+// `streaming`: the tile's source is an HBM-resident matrix (payoffs / staged terminals), so tiles
+// are sized for bandwidth (>= 64 KiB of input each, a few thousand CTAs) instead of for
+// load-balancing a compute-bound simulation.
+static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n, bool streaming = false) {
   TilePlan p;
   p.chunk_w = static_cast<int>(std::min<int64_t>(n, CF_BLOCK));
   p.lanes_r = CF_BLOCK / p.chunk_w;
   const int64_t R = p.lanes_r;
-  int64_t want = (n_contracts * rows_local + TARGET_TILES - 1) / TARGET_TILES;
+  const int64_t target = streaming ? STREAM_TILES : TARGET_TILES;
+  int64_t want = (n_contracts * rows_local + target - 1) / target;
+  if (streaming) want = std::max<int64_t>(want, (16384 + n - 1) / n);  // >= 16 Ki elements per tile
   want = std::max<int64_t>(want, 1);
   p.tile_rows = (want + R - 1) / R * R;
   p.tile_rows = std::min<int64_t>(p.tile_rows, (rows_local + R - 1) / R * R);
@@ -551,11 +557,10 @@ static TileParams base_params(const smc_fused_args* a, const TilePlan& plan) {
 }
 
 // contracts per pass of the single-GPU NORMALIZE path, given the bytes left for staging
-static int64_t normalize_chunk(const smc_fused_args* a, const TilePlan& plan, size_t avail) {
+static size_t normalize_bytes_per_contract(const smc_fused_args* a, const TilePlan& sim_plan, const TilePlan& pay_plan) {
   const int64_t rows = a->batch_end - a->batch_begin;
-  const size_t per = align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
-                     colsum_bytes(plan, 1, a->network_size) + align_up(plan.tiles * sizeof(double)) + 512;
-  return static_cast<int64_t>(avail / per);
+  return align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
+         colsum_bytes(pay_plan, 1, a->network_size) + align_up(sim_plan.tiles * sizeof(double)) + 512;
 }
 
 }  // namespace smc
@@ -568,8 +573,7 @@ extern "C" size_t smc_cf_fused_workspace_bytes(const smc_fused_args* a) {
   const TilePlan plan = make_plan(a->n_contracts, rows, a->network_size);
   if (a->normalization == SMC_RAW) return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
   // NORMALIZE: stage terminals; cap the staging at 8 GiB by chunking contracts
-  const size_t per = align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
-                     colsum_bytes(plan, 1, a->network_size) + align_up(plan.tiles * sizeof(double)) + 512;
+  const size_t per = normalize_bytes_per_contract(a, plan, make_plan(a->n_contracts, rows, a->network_size, true));
   const size_t cap = size_t(8) << 30;
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(a->n_contracts, static_cast<int64_t>(cap / per)));
   return per * chunk + align_up(a->n_contracts * sizeof(double)) + 256;
@@ -580,7 +584,8 @@ extern "C" int smc_cf_fused_launch_count(const smc_fused_args* a) {
   const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
   const int reduce = plan.tiles > MAX_GROUPS ? 1 : 0;
   if (a->normalization == SMC_RAW) return 3 + reduce;  // prep + tile + [reduce] + finalize
-  return 6 + reduce;  // (prep + terminal tile) + terminal sum + (prep + payoff tile) + [reduce] + finalize (per chunk)
+  const int reduce_pay = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, true).tiles > MAX_GROUPS ? 1 : 0;
+  return 6 + reduce_pay;  // (prep + terminal tile) + terminal sum + (prep + payoff tile) + [reduce] + finalize (per chunk)
 }
 
 template <typename Real>
@@ -609,9 +614,11 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
     return set_error(SMC_EINVAL,
                      "smc_cf_fused: NORMALIZE over a batch shard needs the global terminal mean; use "
                      "smc_fused_terminal + allreduce + smc_cf_from_terminal");
+  const TilePlan pay_plan = make_plan(a->n_contracts, rows, n, true);
   double* term_sum = w.take<double>(a->n_contracts);
   const size_t avail = ws_bytes > w.used ? ws_bytes - w.used : 0;
-  const int64_t chunk = std::min<int64_t>(a->n_contracts, normalize_chunk(a, plan, avail));
+  const int64_t chunk = std::min<int64_t>(
+      a->n_contracts, static_cast<int64_t>(avail / normalize_bytes_per_contract(a, plan, pay_plan)));
   if (chunk < 1) return set_error(SMC_EWORKSPACE, "smc_cf_fused: workspace %zu too small for one contract", ws_bytes);
   const size_t mark = w.used;
   for (int64_t c0 = 0; c0 < a->n_contracts; c0 += chunk) {
@@ -621,20 +628,22 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
     p.contract0 = c0;
     Real* staging = w.take<Real>(cc * p.paths_local);
     p.term_partial = w.take<double>(cc * plan.tiles);
-    p.partial = w.take<double>(cc * plan.tiles * n);
+    double* partial = w.take<double>(cc * pay_plan.tiles * n);
     SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(cc * CONSTS_STRIDE));
-    double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(cc * plan.groups * n) : nullptr;
+    double* grouped = pay_plan.tiles > MAX_GROUPS ? w.take<double>(cc * pay_plan.groups * n) : nullptr;
     double* spill = finalize_plan(n).mode == 2 ? w.take<double>(cc * n) : nullptr;
     p.terminal_out = staging;
     if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, cc, a->scheme, consts, st)) return e;
     terminal_sum_kernel<<<static_cast<unsigned>(cc), CF_BLOCK, 0, st>>>(p.term_partial, term_sum + c0, plan.tiles);
     SMC_LAUNCH_OK("terminal_sum_kernel");
-    p.terminal_in = staging;
-    p.terminal_out = nullptr;
-    p.terminal_sum = term_sum + c0;
-    p.normalize = 1;
-    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, cc, a->scheme, consts, st)) return e;
-    if (int e = reduce_and_finalize<Real>(plan, p.partial, grouped, cc, n, scale, cf_out, c0, spill, st)) return e;
+    TileParams pb = base_params(a, pay_plan);
+    pb.contract0 = c0;
+    pb.partial = partial;
+    pb.terminal_in = staging;
+    pb.terminal_sum = term_sum + c0;
+    pb.normalize = 1;
+    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(pb, cc, a->scheme, consts, st)) return e;
+    if (int e = reduce_and_finalize<Real>(pay_plan, partial, grouped, cc, n, scale, cf_out, c0, spill, st)) return e;
   }
   return SMC_OK;
 }
@@ -685,7 +694,7 @@ extern "C" int smc_fused_terminal(const smc_fused_args* a, void* terminal, doubl
 
 extern "C" size_t smc_cf_from_terminal_workspace_bytes(const smc_fused_args* a) {
   if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, true);
   return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
 }
 
@@ -693,7 +702,7 @@ template <typename Real>
 static int cf_from_terminal_impl(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
                                  void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = a->network_size;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n);
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n, true);
   if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
     return set_error(SMC_EWORKSPACE, "smc_cf_from_terminal: workspace too small");
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};
@@ -726,7 +735,7 @@ extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* termina
 extern "C" size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t n, int method) {
   if (batches <= 0 || n <= 0) return 0;
   if (method == SMC_CF_ROW_FFT && rowfft_supported(n)) return rowfft_workspace_bytes(batches, n);
-  return colsum_bytes(make_plan(1, batches, n), 1, n) + 256;
+  return colsum_bytes(make_plan(1, batches, n, true), 1, n) + 256;
 }
 
 extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int dtype, int method, void* out,
@@ -737,7 +746,7 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_cf_fft_mean: invalid dtype %d", dtype);
   SMC_REQUIRE(method == SMC_CF_MEAN_THEN_FFT || method == SMC_CF_ROW_FFT, "smc_cf_fft_mean: invalid method %d", method);
   if (method == SMC_CF_ROW_FFT) return rowfft_mean(mat, batches, n, dtype, out, ws, ws_bytes, as_stream(stream));
-  const TilePlan plan = make_plan(1, batches, n);
+  const TilePlan plan = make_plan(1, batches, n, true);
   if (ws_bytes < colsum_bytes(plan, 1, n)) return set_error(SMC_EWORKSPACE, "smc_cf_fft_mean: workspace too small");
   cudaStream_t st = as_stream(stream);
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};

@@ -185,3 +185,27 @@ def test_full_size_properties() -> None:
     lhs = call.double().mean().item() - put.double().mean().item()
     rhs = float(np.exp(-0.05)) * (term.double().mean().item() - 100.0)
     assert abs(lhs - rhs) <= 1e-5 * abs(rhs) + 1e-6
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_headline_shape_parity_subrun(dtype) -> None:
+    """BASELINE config c2's shape (T=252, N=128) at B=512 with injected NumPy normals (the kind of
+    draws the golden fixtures hold): every stored path value and the CF against the oracle."""
+    T, N, B = 252, 128, 512
+    z = np.random.default_rng(2024).standard_normal((T, N * B)).astype(dtype)
+    c = ogbm.Contract(100.0, 100.0, 1.0, 0.05, 0.0, 0.2)
+    for norm in (ogbm.RAW, ogbm.NORMALIZE):
+        sr = ogbm.simulate(c, z.copy(), normalization=norm)
+        pr = ogbm.price(c, sr)
+        ref_cf = ogbm.cf_estimate(pr.put_price, B, N)
+        io = torch.from_numpy(z.copy()).cuda()
+        _cabi.gbm_paths_inplace(io, 1.0 / T, 100.0, 0.05, 0.0, 0.2, _cabi.SMC_LOG_EULER, 256)
+        if norm == ogbm.NORMALIZE:
+            _cabi.normalize_rows(io, torch.from_numpy(sr.forwards).cuda())
+        assert rel_elem(io.cpu().numpy(), sr.sims) <= _tol(dtype)
+        put, _ = _cabi.payoff(io[-1], 100.0, float(sr.df[-1]))
+        cf = _cabi.cf_fft_mean(put.view(B, N)).cpu().numpy()
+        assert rel_max(cf, ref_cf) <= _tol(dtype)
+        if N >= 32:
+            cf_row = _cabi.cf_fft_mean(put.view(B, N), _cabi.SMC_CF_ROW_FFT).cpu().numpy()
+            assert rel_max(cf_row, ref_cf) <= _tol(dtype)
