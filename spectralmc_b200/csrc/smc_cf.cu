@@ -279,13 +279,38 @@ __global__ void __launch_bounds__(CF_BLOCK) tile_kernel(const TileParams p) {
   }
 }
 
-// level 1: groups of tile partials -> [contracts, groups, n]
+// level 1: groups of tile partials -> [contracts, groups, n].  When n <= 128 the CTA's 256 threads
+// split into `subs` lanes per column, each summing every subs-th tile of the group; the lanes are
+// folded in shared memory in a fixed order.
 __global__ void __launch_bounds__(CF_BLOCK)
     reduce_tiles_kernel(const double* __restrict__ partial, double* __restrict__ grouped, int64_t tiles,
-                        int64_t tiles_per_group, int64_t groups, int64_t n) {
+                        int64_t tiles_per_group, int64_t groups, int64_t n, int subs) {
+  __shared__ double sm[CF_BLOCK];
   const int64_t c = blockIdx.x / groups, g = blockIdx.x - c * groups;
   const int64_t t0 = g * tiles_per_group, t1 = min(t0 + tiles_per_group, tiles);
   const double* src = partial + c * tiles * n;
+  if (subs > 1) {  // n * subs == CF_BLOCK
+    const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
+    double s = 0.0;
+    int64_t t = t0 + sub;
+    for (; t + 3 * subs < t1; t += 4 * subs) {
+      const double a = src[t * n + col], b = src[(t + subs) * n + col];
+      const double cc = src[(t + 2 * subs) * n + col], d = src[(t + 3 * subs) * n + col];
+      s += a;
+      s += b;
+      s += cc;
+      s += d;
+    }
+    for (; t < t1; t += subs) s += src[t * n + col];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (sub == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < subs; ++k) tot += sm[k * n + col];
+      grouped[(c * groups + g) * n + col] = tot;
+    }
+    return;
+  }
   for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
     double s = 0.0;
     int64_t t = t0;
@@ -487,8 +512,9 @@ static int reduce_and_finalize(const TilePlan& plan, double* partial, double* gr
   int64_t groups = plan.tiles;
   if (plan.tiles > MAX_GROUPS) {
     const unsigned grid = static_cast<unsigned>(plan.groups * contracts);
+    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
     reduce_tiles_kernel<<<grid, CF_BLOCK, 0, st>>>(partial, grouped, plan.tiles, plan.tiles_per_group,
-                                                    plan.groups, n);
+                                                    plan.groups, n, subs);
     SMC_LAUNCH_OK("reduce_tiles_kernel");
     vecs = grouped;
     groups = plan.groups;
