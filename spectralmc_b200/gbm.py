@@ -229,7 +229,7 @@ class BlackScholes:
         # The materialised pool is created on first use: the fused path never needs it, and at
         # production sizes one matrix is gigabytes.
         self._ngen: Result[ConcurrentNormGenerator, object] | None = None
-        self._host_cache: tuple[int, float, float] | None = None  # (id(sims), F, df_last)
+        self._host_cache: tuple[tuple[int, int], float, float] | None = None  # ((sims ptr, forwards ptr), F, df_last)
         self._workspace: torch.Tensor | None = None
 
     # ----------------------------------------------------------------- normal supply
@@ -299,7 +299,7 @@ class BlackScholes:
                 _cabi.normalize_rows(sims, forwards.contiguous())  # gbm.py:437-438
         except _cabi.SmcError as exc:
             return Failure(DeviceKernelFailed(status=exc.code, message=exc.message))
-        self._host_cache = (id(sims), float(forwards_h[-1]), float(df_h[-1]))
+        self._host_cache = ((sims.data_ptr(), forwards.data_ptr()), float(forwards_h[-1]), float(df_h[-1]))
         made = validate_model(self.SimResults, times=times, sims=sims, forwards=forwards, df=df)
         if isinstance(made, Failure):
             raise AssertionError(f"SimResults validation failed: {made.error}")
@@ -313,7 +313,7 @@ class BlackScholes:
         if isinstance(sim_result, Failure):
             return sim_result
         sr = sim_result.value
-        if self._host_cache is not None and self._host_cache[0] == id(sr.sims):
+        if self._host_cache is not None and self._host_cache[0] == (sr.sims.data_ptr(), sr.forwards.data_ptr()):
             F_h, df_h = self._host_cache[1], self._host_cache[2]
         else:  # foreign SimResults: one small device->host read
             F_h, df_h = float(sr.forwards[-1].item()), float(sr.df[-1].item())

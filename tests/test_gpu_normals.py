@@ -162,3 +162,45 @@ def test_diagnostics(precision) -> None:
     torch.cuda.synchronize()
     assert gen.get_idle_time() >= idle_before
     assert gen.dtype == precision.to_torch()
+
+
+def test_block_structure_leaves_no_statistical_trace() -> None:
+    """The six normals of a float32 block come from disjoint bit fields of one Philox block; check
+    on 25M draws that each row position has unit moments and that rows inside a block — in
+    particular the (cos, sin) partners and rows sharing a Philox word — are uncorrelated, also in
+    their squares (radius dependence shows up there)."""
+    rows, cols = 12, 1 << 21
+    out = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    _cabi.philox_normals(out, 2024, 5)
+    z = out.double()
+    n = cols
+    for i in range(6):
+        r = z[i]
+        assert abs(r.mean().item()) < 5 / n**0.5, i
+        assert abs(r.var().item() - 1) < 5 * (2 / n) ** 0.5, i
+        assert abs((r**3).mean().item()) < 5 * (15 / n) ** 0.5, i
+        assert abs((r**4).mean().item() - 3) < 5 * (96 / n) ** 0.5, i
+    zc = z[:6] - z[:6].mean(dim=1, keepdim=True)
+    corr = (zc @ zc.T / n).cpu().numpy()
+    sq = z[:6] ** 2 - 1.0
+    corr_sq = (sq @ sq.T / n / 2.0).cpu().numpy()  # var(z^2) = 2
+    off = ~np.eye(6, dtype=bool)
+    assert np.max(np.abs(corr[off])) < 5 / n**0.5
+    # partners of one pair share the radius: z0^2 + z1^2 = r^2 is chi2(2) => corr(z0^2, z1^2) = 0 for exact Box-Muller
+    assert np.max(np.abs(corr_sq[off])) < 6 / n**0.5
+    # consecutive blocks (rows 5 and 6) and consecutive columns are uncorrelated
+    assert abs((z[5] * z[6]).mean().item()) < 5 / n**0.5
+    assert abs((z[0, :-1] * z[0, 1:]).mean().item()) < 5 / n**0.5
+
+
+def test_uniformity_of_the_sum_over_a_path() -> None:
+    """Sum of T=252 normals of a path / sqrt(T) is N(0,1): KS test over 1M paths (what the
+    log-Euler terminal price actually consumes)."""
+    from scipy import stats
+
+    T, P = 252, 1 << 20
+    out = torch.empty((T, P), dtype=torch.float32, device="cuda")
+    _cabi.philox_normals(out, 99, 0)
+    s = (out.double().sum(dim=0) / T**0.5).cpu().numpy()
+    assert stats.kstest(s, "norm").pvalue > 1e-3
+    assert abs(s.std() - 1) < 5 / (2 * P) ** 0.5
