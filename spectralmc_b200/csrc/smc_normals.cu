@@ -18,36 +18,57 @@ constexpr int NORMALS_BLOCK = 256;
 constexpr int GROUPS_PER_THREAD = 4;  // row groups walked by one thread (24 rows f32 / 8 rows f64)
 
 template <int VEC>
+struct StoreVec;
+template <>
+struct StoreVec<1> {
+  static __device__ __forceinline__ void st(float* p, const float (&z)[1][6], int r) { __stcs(p, z[0][r]); }
+};
+template <>
+struct StoreVec<2> {
+  static __device__ __forceinline__ void st(float* p, const float (&z)[2][6], int r) {
+    __stcs(reinterpret_cast<float2*>(p), make_float2(z[0][r], z[1][r]));
+  }
+};
+template <>
+struct StoreVec<4> {
+  static __device__ __forceinline__ void st(float* p, const float (&z)[4][6], int r) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(z[0][r], z[1][r], z[2][r], z[3][r]));
+  }
+};
+
+// grid.x covers column groups, grid.y covers runs of `groups_per_cta` row groups.  Full 6-row
+// groups take the unguarded fast path (pointer bumped by `cols` per row); only the last group of a
+// matrix whose row count is not a multiple of 6 checks rows.
+template <int VEC>
 __global__ void __launch_bounds__(NORMALS_BLOCK, 4)
     philox_normals_f32_kernel(float* __restrict__ out, int64_t rows, int64_t cols, PhiloxKeys key,
-                              uint32_t k_lo, uint32_t k_hi) {
+                              uint32_t k_lo, uint32_t k_hi, int groups_per_cta) {
   const int64_t col0 = (static_cast<int64_t>(blockIdx.x) * NORMALS_BLOCK + threadIdx.x) * VEC;
   if (col0 >= cols) return;
-  const int64_t nq = (rows + 5) / 6;
-  for (int64_t q0 = static_cast<int64_t>(blockIdx.y) * GROUPS_PER_THREAD; q0 < nq;
-       q0 += static_cast<int64_t>(gridDim.y) * GROUPS_PER_THREAD) {
-#pragma unroll 1
-    for (int g = 0; g < GROUPS_PER_THREAD; ++g) {
-      const int64_t q = q0 + g;
-      if (q >= nq) break;
-      float z[VEC][6];
+  const int64_t nq = (rows + 5) / 6, full = rows / 6;
+  const int64_t q_begin = static_cast<int64_t>(blockIdx.y) * groups_per_cta;
+  const int64_t q_end = min(q_begin + groups_per_cta, nq);
+  float* dst = out + 6 * q_begin * cols + col0;
+  const uint32_t c = static_cast<uint32_t>(col0);
+  int64_t q = q_begin;
+  for (; q < min(q_end, full); ++q) {
+    float z[VEC][6];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (VEC == 1 || col0 + v < cols)
-          normals6_f32(static_cast<uint32_t>(col0 + v), static_cast<uint32_t>(q), k_lo, k_hi, key, z[v]);
-      }
+    for (int v = 0; v < VEC; ++v) normals6_f32(c + v, static_cast<uint32_t>(q), k_lo, k_hi, key, z[v]);
 #pragma unroll
-      for (int rr = 0; rr < 6; ++rr) {
-        const int64_t row = 6 * q + rr;
-        if (row < rows) {
-          float* dst = out + row * cols + col0;
-          if (VEC == 4) {
-            __stcs(reinterpret_cast<float4*>(dst), make_float4(z[0][rr], z[1][rr], z[2][rr], z[3][rr]));
-          } else {
-            __stcs(dst, z[0][rr]);
-          }
-        }
-      }
+    for (int rr = 0; rr < 6; ++rr) {
+      StoreVec<VEC>::st(dst, z, rr);
+      dst += cols;
+    }
+  }
+  if (q < q_end) {  // ragged last group
+    float z[VEC][6];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) normals6_f32(c + v, static_cast<uint32_t>(q), k_lo, k_hi, key, z[v]);
+#pragma unroll
+    for (int rr = 0; rr < 5; ++rr) {
+      if (6 * q + rr < rows) StoreVec<VEC>::st(dst, z, rr);
+      dst += cols;
     }
   }
 }
@@ -106,18 +127,29 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
   const uint32_t k_hi = static_cast<uint32_t>(matrix_index >> 32);
   cudaStream_t st = as_stream(stream);
   const bool aligned16 = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
-  const char* force_scalar = std::getenv("SMC_NORMALS_SCALAR");  // tuning knob
-  const bool allow_vec = !(force_scalar && force_scalar[0] == '1');
+  // tuning knob: SMC_NORMALS_VEC=1|2|4 caps the float32 store width
+  const char* vec_env = std::getenv("SMC_NORMALS_VEC");
+  const int vec_cap = vec_env ? std::atoi(vec_env) : 4;
+  const bool allow_vec = vec_cap > 1;
   if (dtype == SMC_F32) {
-    const bool vec = allow_vec && aligned16 && (cols % 4 == 0);
-    const int v = vec ? 4 : 1;
+    const bool a8 = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+    int v = 1;
+    if (vec_cap >= 4 && aligned16 && cols % 4 == 0) v = 4;
+    else if (vec_cap >= 2 && a8 && cols % 2 == 0) v = 2;
     const int64_t nq = (rows + 5) / 6;
-    dim3 grid(static_cast<unsigned>((cols / v + (cols % v != 0) + NORMALS_BLOCK - 1) / NORMALS_BLOCK),
-              static_cast<unsigned>(std::min<int64_t>((nq + GROUPS_PER_THREAD - 1) / GROUPS_PER_THREAD, 65535)));
-    if (vec)
-      philox_normals_f32_kernel<4><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi);
+    // enough CTAs along y to fill the machine for narrow matrices, long runs for wide ones
+    const int64_t col_ctas = (cols / v + NORMALS_BLOCK - 1) / NORMALS_BLOCK;
+    int groups_per_cta = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, (col_ctas * nq + 4735) / 4736)));
+    groups_per_cta = std::min(groups_per_cta, 8);
+    const int64_t gy = (nq + groups_per_cta - 1) / groups_per_cta;
+    SMC_REQUIRE(gy <= 65535, "smc_philox_normals: too many rows (%lld) for one launch", (long long)rows);
+    dim3 grid(static_cast<unsigned>(col_ctas), static_cast<unsigned>(gy));
+    if (v == 4)
+      philox_normals_f32_kernel<4><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi, groups_per_cta);
+    else if (v == 2)
+      philox_normals_f32_kernel<2><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi, groups_per_cta);
     else
-      philox_normals_f32_kernel<1><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi);
+      philox_normals_f32_kernel<1><<<grid, NORMALS_BLOCK, 0, st>>>(static_cast<float*>(out), rows, cols, key, k_lo, k_hi, groups_per_cta);
   } else {
     const bool vec = allow_vec && aligned16 && (cols % 2 == 0);
     const int v = vec ? 2 : 1;

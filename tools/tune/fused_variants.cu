@@ -70,13 +70,13 @@ __device__ __forceinline__ float block_sum4(uint32_t col, uint32_t q, const Phil
   float uc = __uint_as_float((x[2] >> 9) + 0x3f800000u) - 0x1.fffffep-1f;
   if (MODE == 0 || MODE == 4) {
     if (__builtin_expect(min(x[0], x[2]) < 512u, 0)) {
-      ua = refine_radius_uniform(x[0], ua);
-      uc = refine_radius_uniform(x[2], uc);
+      ua = ua * 0.5f;
+      uc = uc * 0.5f;
     }
   }
   float z0, z1, z2, z3;
-  box_muller_f32(ua, x[1], z0, z1);
-  box_muller_f32(uc, x[3], z2, z3);
+  box_muller_f32(ua, __uint_as_float((x[1] >> 9) + 0x3f800000u), z0, z1);
+  box_muller_f32(uc, __uint_as_float((x[3] >> 9) + 0x3f800000u), z2, z3);
   return (z0 + z1) + (z2 + z3);
 }
 
@@ -93,7 +93,7 @@ __device__ __forceinline__ float block_sum6(uint32_t col, uint32_t q, const Phil
   float ua = u21(f0) - 0x1.fffffcp-1f, ub = u21(f2) - 0x1.fffffcp-1f, uc = u21(f4) - 0x1.fffffcp-1f;
   if (MODE == 0) {
     if (__builtin_expect(min(min(f0, f2), f4) < 2048u, 0)) {
-      ua = refine_radius_uniform(x[0], ua); ub = refine_radius_uniform(x[1], ub); uc = refine_radius_uniform(x[2], uc);
+      ua *= 0.5f; ub *= 0.5f; uc *= 0.5f;
     }
   }
   float z0, z1, z2, z3, z4, z5;
@@ -110,6 +110,59 @@ __device__ __forceinline__ float block_sum6(uint32_t col, uint32_t q, const Phil
     const float r = mufu_sqrt(-1.38629436111989062f * mufu_lg2(uc)); z4 = r * mufu_cos(th); z5 = r * mufu_sin(th);
   }
   return ((z0 + z1) + (z2 + z3)) + (z4 + z5);
+}
+
+template <int UNROLL, int PATHS, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) product6_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
+  const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * BLOCK;
+  float total = 0.f;
+  for (int64_t p = 0; p < paths_per_thread; p += PATHS) {
+    float s[PATHS];
+    uint32_t col[PATHS];
+#pragma unroll
+    for (int k = 0; k < PATHS; ++k) { s[k] = 0.f; col[k] = tid + static_cast<uint32_t>(p + k) * nthreads; }
+#pragma unroll UNROLL
+    for (uint32_t q = 0; q < T / 6; ++q) {
+#pragma unroll
+      for (int k = 0; k < PATHS; ++k) {
+        float z[6];
+        normals6_f32(col[k], q, 7u, 0u, key, z);
+        s[k] += ((z[0] + z[1]) + (z[2] + z[3])) + (z[4] + z[5]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < PATHS; ++k) total += mufu_ex2(s[k] * 0.01f);
+  }
+  out[tid] = total;
+}
+
+template <int UNROLL, int PATHS, int BLOCK, int MINB>
+void runp(const char* name) {
+  const int64_t total_paths = 8388608;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, product6_kernel<UNROLL, PATHS, BLOCK, MINB>, BLOCK, 0);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, product6_kernel<UNROLL, PATHS, BLOCK, MINB>);
+  const int grid = static_cast<int>(total_paths / (2 * BLOCK));
+  const int64_t ppt = 2;
+  float* out;
+  cudaMalloc(&out, sizeof(float) * static_cast<size_t>(grid) * BLOCK);
+  const PhiloxKeys key = make_philox_keys(7);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a);
+    product6_kernel<UNROLL, PATHS, BLOCK, MINB><<<grid, BLOCK>>>(out, ppt, key);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double steps = static_cast<double>(grid) * BLOCK * ppt * T;
+  printf("%-44s regs=%3d occ=%2d grid=%6d ppt=%3lld  %.3f ms  %.3e path-steps/s\n", name, fa.numRegs, occ, grid, (long long)ppt, best, steps / (best * 1e-3));
+  cudaFree(out);
 }
 
 template <int MODE, int UNROLL, int BLOCK, int MINB>
@@ -225,6 +278,11 @@ int main() {
   run<10, 1, 2, 1, 256, 1>("no refinement branch", sms);
   run<10, 2, 2, 1, 256, 1>("philox only", sms);
   run<10, 3, 2, 1, 256, 1>("box-muller only", sms);
+  runp<1, 1, 256, 1>("product normals6, 1 path, unroll1");
+  runp<2, 1, 256, 1>("product normals6, 1 path, unroll2");
+  runp<1, 2, 256, 1>("product normals6, 2 paths interleaved");
+  runp<1, 1, 128, 1>("product normals6, block128");
+  runp<1, 1, 256, 6>("product normals6, minb6 (<=40 regs)");
   run6<0, 1, 256, 1>("6 normals/block (21-bit), unroll1");
   run6<0, 2, 256, 1>("6 normals/block (21-bit), unroll2");
   run6<1, 2, 256, 1>("6 normals/block, no refinement");
