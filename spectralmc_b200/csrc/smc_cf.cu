@@ -170,7 +170,7 @@ __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, ui
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
   float acc = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
   const uint32_t nq = static_cast<uint32_t>(timesteps / 6);
-#pragma unroll 2
+#pragma unroll 1  // unroll 2 costs registers: under a 5-CTA cap ptxas rematerialises and the loop grows 18 %
   for (uint32_t q = 0; q < nq; ++q) {
     float z[6];
     normals6_f32(col, q, k_lo, k_hi, keys, z);
@@ -209,10 +209,13 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
   return acc;
 }
 
-// float32 fused instantiations are capped at 51 registers (5 CTAs = 40 warps per SM); the
-// microbenchmark shows the 2x-unrolled loop is ~2 % faster only if occupancy does not drop
+#ifndef SMC_F64_FUSED_MIN_CTAS
+#define SMC_F64_FUSED_MIN_CTAS 4
+#endif
+// float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
+// registers and run 2 CTAs per SM
 template <typename Real, int SRC, int SCHEME, int OUT>
-__global__ void __launch_bounds__(CF_BLOCK, (sizeof(Real) == 4 && SRC == SRC_FUSED) ? 5 : 1)
+__global__ void __launch_bounds__(CF_BLOCK, (SRC == SRC_FUSED && sizeof(Real) == 8) ? SMC_F64_FUSED_MIN_CTAS : 0)
     tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
   const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;

@@ -152,6 +152,59 @@ __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t 
 }
 
 // ---- float64 block: 4 words -> 1 pair --------------------------------------------------
+// log / sincospi specialised to the arguments Box–Muller produces (u in (0,1), a normal number;
+// |angle / pi| <= 1), with the polynomial coefficients in __constant__ memory so each DFMA takes
+// its coefficient as a constant-bank operand.  libdevice's general-purpose versions made ptxas
+// rebuild ~40 64-bit literals per iteration (80 of 240 issue slots of the float64 loop).  The
+// polynomials are the classical minimax sets of Sun's FDLIBM (k_sin.c, k_cos.c, e_log.c; error
+// < 1 ulp); tests/test_gpu_normals.py holds the device output to 1e-13 of the float64 oracle.
+static __constant__ double kSinCoef[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                          -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                          -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double kCosCoef[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03,
+                                          2.48015872894767294178e-05,  -2.75573143513906633035e-07,
+                                          2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+static __constant__ double kLogCoef[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                          2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                          1.479819860511658591e-01};
+static __constant__ double kLogMisc[4] = {6.93147180369123816490e-01 /* ln2 hi */, 1.90821492927058770002e-10 /* ln2 lo */,
+                                          3.14159265358979311600e+00 /* pi hi */, 1.22464679914735317723e-16 /* pi lo */};
+
+// natural log of u in (0, 1), u normal
+__device__ __forceinline__ double log_unit_interval(double u) {
+  int hi = __double2hiint(u);
+  const int lo = __double2loint(u);
+  int k = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;  // m in [1, 2)
+  if (hi > 0x3ff6a09e) {                // m > sqrt(2): use m / 2
+    hi -= 0x00100000;
+    k += 1;
+  }
+  const double f = __hiloint2double(hi, lo) - 1.0;
+  const double s = f / (2.0 + f);
+  const double z = s * s, w = z * z;
+  const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
+  const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
+  const double R = t1 + t2, hfsq = 0.5 * f * f, dk = static_cast<double>(k);
+  return dk * kLogMisc[0] - ((hfsq - fma(s, hfsq + R, dk * kLogMisc[1])) - f);
+}
+
+// sin(pi t), cos(pi t) for |t| <= 1
+__device__ __forceinline__ void sincospi_unit(double t, double& sn, double& cs) {
+  const double n = rint(2.0 * t);             // quadrant, in {-2 .. 2}
+  const double r = fma(n, -0.5, t);           // exact, |r| <= 1/4
+  const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);  // pi r, two-term pi
+  const double z = x * x;
+  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
+  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);
+  const double s0 = fma(x * z, ps, x);                 // sin x
+  const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));  // cos x
+  const int q = static_cast<int>(n) & 3;
+  const double a = (q & 1) ? c0 : s0, b = (q & 1) ? s0 : c0;
+  sn = (q & 2) ? -a : a;                       // q: 0 -> s, 1 -> c, 2 -> -s, 3 -> -c
+  cs = ((q + 1) & 2) ? -b : b;                 // q: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
+}
+
 __device__ __forceinline__ void normals2_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                              const PhiloxKeys& key, double (&z)[2]) {
   uint32_t x[4];
@@ -163,9 +216,9 @@ __device__ __forceinline__ void normals2_f64(uint32_t col, uint32_t q, uint32_t 
   const double w =
       __hiloint2double(static_cast<int>((x[2] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[3])) -
       1.5;  // u2 - 0.5 - 2^-53
-  const double r = sqrt(-2.0 * log(u1));
+  const double r = sqrt(-2.0 * log_unit_interval(u1));
   double s, c;
-  sincospi(2.0 * w + 0x1p-52, &s, &c);  // angle / pi = 2 (u2 - 0.5), exact
+  sincospi_unit(2.0 * w + 0x1p-52, s, c);  // angle / pi = 2 (u2 - 0.5), exact
   z[0] = r * c;
   z[1] = r * s;
 }
