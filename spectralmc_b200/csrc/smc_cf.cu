@@ -194,6 +194,11 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
                                                     const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
   double acc = SCHEME == SMC_LOG_EULER ? 0.0 : k.X0;
   const uint32_t nq = static_cast<uint32_t>(timesteps >> 1);
+#ifndef SMC_F64_UNROLL
+#define SMC_F64_UNROLL 1
+#endif
+  constexpr int kUnroll = SMC_F64_UNROLL;
+#pragma unroll kUnroll
   for (uint32_t q = 0; q < nq; ++q) {
     double z[2];
     normals2_f64(col, q, k_lo, k_hi, keys, z);

@@ -209,3 +209,17 @@ def test_full_size_headline_config_statistics() -> None:
     assert np.sqrt(np.mean(np.abs(cf[1:]) ** 2)) > 0.3 * noise
     # Hermitian symmetry of the DFT of a real vector
     assert np.max(np.abs(cf[1:] - np.conj(cf[1:][::-1]))) <= 1e-5 * abs(cf[0])
+
+
+@pytest.mark.parametrize("C,T,N,B", [(4096, 12, 128, 8), (70000, 1, 16, 16)])
+def test_many_contracts_in_one_call(C, T, N, B) -> None:
+    """c5-like contract counts (and > 65 535, which spills into gridDim.z): sampled contracts of the
+    batch equal single-contract calls at the matching matrix index."""
+    rows = sobol_contracts(C, seed=3)
+    big = _fused(rows, T, N, B, torch.float32, 11, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    assert np.all(np.isfinite(big))
+    for c in (0, 1, C // 2, 65535 if C > 65536 else C // 3, C - 1):
+        one = _fused(rows[c : c + 1], T, N, B, torch.float32, 11, c, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+        assert np.array_equal(big[c], one[0]) or rel_max(big[c], one[0]) <= 1e-6, c
+    norm = _fused(rows[:300], T, N, B, torch.float32, 11, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_NORMALIZE)
+    assert np.all(np.isfinite(norm))
