@@ -165,28 +165,59 @@ __device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>
 
 // terminal price of global path `col` of the matrix (k_lo, k_hi): every one of the `timesteps`
 // normals is drawn and consumed.
-template <int SCHEME>
-__device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
-                                                   const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
+template <int SCHEME, bool REFINE>
+__device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
+                                                   const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi,
+                                                   uint32_t& min_word) {
   float acc = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
   const uint32_t nq = static_cast<uint32_t>(timesteps / 6);
 #pragma unroll 1  // unroll 2 costs registers: under a 5-CTA cap ptxas rematerialises and the loop grows 18 %
   for (uint32_t q = 0; q < nq; ++q) {
     float z[6];
-    normals6_f32(col, q, k_lo, k_hi, keys, z);
+    normals6_f32_impl<REFINE>(col, q, k_lo, k_hi, keys, z, min_word);
 #pragma unroll
     for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
   }
   const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
   if (rem) {
     float z[6];
-    normals6_f32(col, nq, k_lo, k_hi, keys, z);
+    normals6_f32_impl<REFINE>(col, nq, k_lo, k_hi, keys, z, min_word);
 #pragma unroll
     for (int u = 0; u < 5; ++u)
       if (u < rem) consume<float, SCHEME>(acc, z[u], k);
   }
   if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
   return acc;
+}
+
+// the rare re-simulation (some block of the path had a zero radius field): same path with the
+// refinement applied.  Arguments by value so the caller keeps its key block in the constant bank.
+template <int SCHEME>
+static __device__ __noinline__ float simulate_path_exact_f32(float X0, float lin0, float lin1, uint32_t col,
+                                                             int64_t timesteps, uint32_t seed_lo, uint32_t seed_hi,
+                                                             uint32_t k_lo, uint32_t k_hi) {
+  PhiloxKeys keys;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    keys.k0[r] = seed_lo + static_cast<uint32_t>(r) * PHILOX_W0;
+    keys.k1[r] = seed_hi + static_cast<uint32_t>(r) * PHILOX_W1;
+  }
+  SimConsts<float> k{};
+  k.X0 = X0;
+  k.lin0 = lin0;
+  k.lin1 = lin1;
+  uint32_t unused = 0;
+  return simulate_path_f32<SCHEME, true>(k, col, timesteps, keys, k_lo, k_hi, unused);
+}
+
+template <int SCHEME>
+__device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
+                                                   const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
+  uint32_t min_word = 0xffffffffu;
+  float v = simulate_path_f32<SCHEME, false>(k, col, timesteps, keys, k_lo, k_hi, min_word);
+  if (__builtin_expect(min_word < 2048u, 0))
+    v = simulate_path_exact_f32<SCHEME>(k.X0, k.lin0, k.lin1, col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
+  return v;
 }
 
 template <int SCHEME>
@@ -217,10 +248,13 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #ifndef SMC_F64_FUSED_MIN_CTAS
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
+#ifndef SMC_F32_FUSED_MIN_CTAS
+#define SMC_F32_FUSED_MIN_CTAS 5  // the rare exact-path callee would otherwise raise the kernel to 72 registers
+#endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
 template <typename Real, int SRC, int SCHEME, int OUT>
-__global__ void __launch_bounds__(CF_BLOCK, (SRC == SRC_FUSED && sizeof(Real) == 8) ? SMC_F64_FUSED_MIN_CTAS : 0)
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS))
     tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
   const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;

@@ -129,19 +129,30 @@ static __device__ __noinline__ float3 refine_radius_uniforms(uint32_t col, uint3
   return make_float3(u0, u1, u2);
 }
 
-// 6 normals for rows 6q .. 6q+5 of column `col` of matrix (k_lo, k_hi)
-__device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
-                                             const PhiloxKeys& key, float (&z)[6]) {
+// 6 normals for rows 6q .. 6q+5 of column `col` of matrix (k_lo, k_hi).
+// REFINE = true is the stream as specified (one rarely-taken branch per block).
+// REFINE = false draws the coarse radius uniform for every pair and only folds the three radius
+// words into `min_word`; a caller that consumes a whole path can test `min_word < 2048` ONCE after
+// its time loop and, in the 6e-5 of paths where some block needed the refinement, redo the path
+// with REFINE = true.  The result is identical to the specified stream; the hot loop loses the
+// compare/branch/reconvergence instructions (5 of 98 issue slots per block).
+template <bool REFINE>
+__device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                                  const PhiloxKeys& key, float (&z)[6], uint32_t& min_word) {
   uint32_t x[4];
   philox4x32_10(col, q, k_lo, k_hi, key, x);
   float u[3];
 #pragma unroll
   for (int p = 0; p < 3; ++p) u[p] = unit_float_21(x[p] >> 9) - 0x1.fffff8p-1f;  // (R + 0.5) 2^-21
-  if (__builtin_expect(min(min(x[0], x[1]), x[2]) < 2048u, 0)) {
-    const float3 f = refine_radius_uniforms(col, q, k_lo, k_hi, key.k0[0], key.k1[0], x[0], x[1], x[2], u[0], u[1], u[2]);
-    u[0] = f.x;
-    u[1] = f.y;
-    u[2] = f.z;
+  if (REFINE) {
+    if (__builtin_expect(min(min(x[0], x[1]), x[2]) < 2048u, 0)) {
+      const float3 f = refine_radius_uniforms(col, q, k_lo, k_hi, key.k0[0], key.k1[0], x[0], x[1], x[2], u[0], u[1], u[2]);
+      u[0] = f.x;
+      u[1] = f.y;
+      u[2] = f.z;
+    }
+  } else {
+    min_word = min(min(min_word, x[0]), min(x[1], x[2]));
   }
   const float a0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
   const float a1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
@@ -149,6 +160,12 @@ __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t 
   box_muller_f32(u[0], a0, z[0], z[1]);
   box_muller_f32(u[1], a1, z[2], z[3]);
   box_muller_f32(u[2], a2, z[4], z[5]);
+}
+
+__device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                             const PhiloxKeys& key, float (&z)[6]) {
+  uint32_t unused = 0;
+  normals6_f32_impl<true>(col, q, k_lo, k_hi, key, z, unused);
 }
 
 // ---- float64 block: 4 words -> 1 pair --------------------------------------------------

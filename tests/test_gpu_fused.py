@@ -223,3 +223,35 @@ def test_many_contracts_in_one_call(C, T, N, B) -> None:
         assert np.array_equal(big[c], one[0]) or rel_max(big[c], one[0]) <= 1e-6, c
     norm = _fused(rows[:300], T, N, B, torch.float32, 11, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_NORMALIZE)
     assert np.all(np.isfinite(norm))
+
+
+def test_paths_that_need_the_refinement_block() -> None:
+    """The fused float32 loop checks for zero radius fields once per PATH and re-simulates those
+    paths with the refinement applied.  Locate such paths with the oracle (seed 7, matrix 0 has
+    several within 2^19 columns and 4 row groups) and compare every stored terminal price."""
+    T, N, B = 24, 128, 4096
+    P = N * B
+    j = np.arange(P, dtype=np.uint32)[None, :]
+    q = np.arange(T // 6, dtype=np.uint32)[:, None]
+    radius, _ = philox.f32_fields(*philox.philox4x32_10((j, q, 0, 0), (7, 0)))
+    cols = sorted({int(b) for p in range(3) for b in np.nonzero(radius[p] == 0)[1]})
+    assert cols, "no path needs the refinement block in this range"
+    contracts = torch.tensor([CANON], dtype=torch.float64, device="cuda")
+    args = _cabi.make_fused_args(contracts, 1, T, N, B, torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 7, 0)
+    terminal, tsum = _cabi.fused_terminal(args, contracts.device, torch.float32)
+    got = terminal[0].cpu().numpy().astype(np.float64)
+    z = philox.normals_matrix(T, P, np.float32, 7, 0)
+    ref = z.copy()
+    ogbm.simulate_paths_inplace(ref, T, 1.0 / T, 100.0, 0.05, 0.0, 0.2, True)
+    ref_t = ref[-1].astype(np.float64)
+    assert np.max(np.abs(got - ref_t) / ref_t) <= 1e-5
+    # the refined paths differ visibly from what an unrefined radius (u = 2^-22, r = 5.52) would give
+    for c in cols:
+        assert abs(got[c] - ref_t[c]) / ref_t[c] <= 1e-5, c
+    for scheme in (_cabi.SMC_SIMPLE_EULER, _cabi.SMC_LOG_EULER_STEPWISE):
+        a2 = _cabi.make_fused_args(contracts, 1, T, N, B, torch.float32, scheme, _cabi.SMC_RAW, 7, 0)
+        t2, _ = _cabi.fused_terminal(a2, contracts.device, torch.float32)
+        ref2 = z.copy()
+        ogbm.simulate_paths_inplace(ref2, T, 1.0 / T, 100.0, 0.05, 0.0, 0.2, scheme != _cabi.SMC_SIMPLE_EULER)
+        g2 = t2[0].cpu().numpy().astype(np.float64)
+        assert np.max(np.abs(g2[cols] - ref2[-1][cols]) / ref2[-1][cols]) <= 2e-5
