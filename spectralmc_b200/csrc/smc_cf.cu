@@ -213,11 +213,18 @@ static __device__ __noinline__ float simulate_path_exact_f32(float X0, float lin
 template <int SCHEME>
 __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
+#ifndef SMC_F32_POSTHOC_REFINE
+#define SMC_F32_POSTHOC_REFINE 1
+#endif
   uint32_t min_word = 0xffffffffu;
+#if SMC_F32_POSTHOC_REFINE
   float v = simulate_path_f32<SCHEME, false>(k, col, timesteps, keys, k_lo, k_hi, min_word);
   if (__builtin_expect(min_word < 2048u, 0))
     v = simulate_path_exact_f32<SCHEME>(k.X0, k.lin0, k.lin1, col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
   return v;
+#else
+  return simulate_path_f32<SCHEME, true>(k, col, timesteps, keys, k_lo, k_hi, min_word);
+#endif
 }
 
 template <int SCHEME>
@@ -249,7 +256,7 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 5  // the rare exact-path callee would otherwise raise the kernel to 72 registers
+#define SMC_F32_FUSED_MIN_CTAS 4  // 64 registers: measured best of {0 (72 regs), 4, 5, 6} at config c2 (1.387 ms vs 1.408-1.425)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM

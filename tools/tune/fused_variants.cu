@@ -112,6 +112,63 @@ __device__ __forceinline__ float block_sum6(uint32_t col, uint32_t q, const Phil
   return ((z0 + z1) + (z2 + z3)) + (z4 + z5);
 }
 
+template <int UNROLL, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) posthoc6_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
+  const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * BLOCK;
+  float total = 0.f;
+  for (int64_t p = 0; p < paths_per_thread; ++p) {
+    float s = 0.f;
+    uint32_t mw = 0xffffffffu;
+    const uint32_t col = tid + static_cast<uint32_t>(p) * nthreads;
+#pragma unroll UNROLL
+    for (uint32_t q = 0; q < T / 6; ++q) {
+      float z[6];
+      normals6_f32_impl<false>(col, q, 7u, 0u, key, z, mw);
+      s += ((z[0] + z[1]) + (z[2] + z[3])) + (z[4] + z[5]);
+    }
+    if (mw < 2048u) {
+      s = 0.f;
+#pragma unroll 1
+      for (uint32_t q = 0; q < T / 6; ++q) {
+        float z[6];
+        normals6_f32(col, q, 7u, 0u, key, z);
+        s += ((z[0] + z[1]) + (z[2] + z[3])) + (z[4] + z[5]);
+      }
+    }
+    total += mufu_ex2(s * 0.01f);
+  }
+  out[tid] = total;
+}
+
+template <int UNROLL, int BLOCK, int MINB>
+void runh(const char* name) {
+  const int64_t total_paths = 8388608;
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, posthoc6_kernel<UNROLL, BLOCK, MINB>, BLOCK, 0);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, posthoc6_kernel<UNROLL, BLOCK, MINB>);
+  const int grid = static_cast<int>(total_paths / (2 * BLOCK));
+  const int64_t ppt = 2;
+  float* out;
+  cudaMalloc(&out, sizeof(float) * static_cast<size_t>(grid) * BLOCK);
+  const PhiloxKeys key = make_philox_keys(7);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(a);
+    posthoc6_kernel<UNROLL, BLOCK, MINB><<<grid, BLOCK>>>(out, ppt, key);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  const double steps = static_cast<double>(grid) * BLOCK * ppt * T;
+  printf("%-44s regs=%3d occ=%2d grid=%6d ppt=%3lld  %.3f ms  %.3e path-steps/s\n", name, fa.numRegs, occ, grid, (long long)ppt, best, steps / (best * 1e-3));
+  cudaFree(out);
+}
+
 template <int UNROLL, int PATHS, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) product6_kernel(float* out, int64_t paths_per_thread, PhiloxKeys key) {
   const uint32_t tid = blockIdx.x * BLOCK + threadIdx.x;
@@ -278,6 +335,11 @@ int main() {
   run<10, 1, 2, 1, 256, 1>("no refinement branch", sms);
   run<10, 2, 2, 1, 256, 1>("philox only", sms);
   run<10, 3, 2, 1, 256, 1>("box-muller only", sms);
+  runh<1, 256, 1>("post-hoc refinement, unroll1");
+  runh<2, 256, 1>("post-hoc refinement, unroll2");
+  runh<1, 256, 5>("post-hoc refinement, unroll1 minb5");
+  runh<1, 256, 6>("post-hoc refinement, unroll1 minb6");
+  runh<1, 128, 1>("post-hoc refinement, block128");
   runp<1, 1, 256, 1>("product normals6, 1 path, unroll1");
   runp<2, 1, 256, 1>("product normals6, 1 path, unroll2");
   runp<1, 2, 256, 1>("product normals6, 2 paths interleaved");
