@@ -60,3 +60,30 @@ for method, name in ((_cabi.SMC_CF_MEAN_THEN_FFT, "cf_fft_mean mean-then-FFT"), 
     print(json.dumps({"what": name, "B": 65536, "N": 128, "ms": ms, "GBps": mat.numel() * 4 / ms / 1e6}), flush=True)
 ms = timeit(lambda: torch.fft.fft(mat, dim=1).mean(dim=0))
 print(json.dumps({"what": "torch.fft.fft(dim=1).mean(dim=0) (cuFFT, the reference's formulation)", "ms": ms, "GBps": mat.numel() * 4 / ms / 1e6}), flush=True)
+
+# c3: Sobol batch of 1024 contracts -> targets -> CVNN (6 -> 32 modReLU -> N) Adam step, through the trainer API
+import time
+
+from spectralmc_b200.cvnn import make_cvnn
+from spectralmc_b200.effects import ForwardNormalization, PathScheme
+from spectralmc_b200.gbm import BlackScholesConfig, SimulationParams
+from spectralmc_b200.gbm_trainer import GbmCVNNPricer, TrainingConfig
+from spectralmc_b200.numerical import Precision
+from spectralmc_b200.sobol_sampler import BoundSpec, build_domain_bounds
+from spectralmc_b200.gbm import BlackScholes
+
+bounds = build_domain_bounds(BlackScholes.Inputs, {k: BoundSpec(*b) for k, b in dict(
+    X0=(0.001, 10_000.0), K=(0.001, 20_000.0), T=(0.0, 10.0), r=(-0.2, 0.2), d=(-0.2, 0.2), v=(0.0, 2.0)).items()}).unwrap()
+for name, T, N, B, steps in (("c3 training step, trainer-test size (T=1,N=16,B=4096)", 1, 16, 4096, 10),
+                             ("c3 training step, c2-size simulation (T=252,N=128,B=65536)", 252, 128, 65536, 2)):
+    sp = SimulationParams(timesteps=T, network_size=N, batches_per_mc_run=B, threads_per_block=256, mc_seed=42, buffer_size=1, dtype=Precision.float32)
+    cfg = BlackScholesConfig(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+    pricer = GbmCVNNPricer(cfg, bounds, make_cvnn(6, N, seed=42))
+    pricer.train(TrainingConfig(num_batches=1, batch_size=1024)).unwrap()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    losses = pricer.train(TrainingConfig(num_batches=steps, batch_size=1024)).unwrap()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    print(json.dumps({"what": name, "ms_per_training_step": dt * 1e3, "contracts_per_step": 1024, "cf_estimates_per_sec": 1024 / dt,
+                      "path_steps_per_sec": 1024.0 * T * N * B / dt, "last_loss": losses[-1]}), flush=True)
