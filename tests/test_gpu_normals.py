@@ -45,11 +45,11 @@ def test_float64_matches_specification(rows, cols) -> None:
 def test_float32_matches_specification(rows, cols) -> None:
     got = _device_matrix(rows, cols, torch.float32, seed=42, k=3).astype(np.float64)
     ref, rad = philox.normals_matrix(rows, cols, np.float32, 42, 3, return_radius=True)
-    tol = 2e-6 * (1 + np.abs(ref)) + 4e-7 / np.maximum(rad, 1e-6)
+    tol = 2e-6 * (1 + np.abs(ref)) + 6e-7 * rad + 4e-7 / np.maximum(rad, 1e-6)
     err = np.abs(got - ref.astype(np.float64))
     assert np.all(err <= tol), float(np.max(err / tol))
     # the bulk is far tighter than the bound
-    assert np.quantile(err, 0.99) <= 2e-6
+    assert np.quantile(err, 0.99) <= 3e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
@@ -78,7 +78,7 @@ def test_refined_tail_entries_match() -> None:
     for qq, col, p in hits:
         for row in (6 * qq + 2 * p, 6 * qq + 2 * p + 1):
             assert rad[row, col] > 5.46
-            assert abs(got[row, col] - ref[row, col]) <= 2e-6 * (1 + abs(ref[row, col])) + 4e-7 / rad[row, col]
+            assert abs(got[row, col] - ref[row, col]) <= 2e-6 * (1 + abs(ref[row, col])) + 6e-7 * rad[row, col] + 4e-7 / rad[row, col]
 
 
 def test_unaligned_output_takes_the_scalar_path() -> None:
