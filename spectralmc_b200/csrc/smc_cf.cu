@@ -21,6 +21,7 @@
 // not depend on the device the job lands on.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "smc_device.cuh"
 #include "smc_internal.h"
@@ -53,7 +54,12 @@ static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n, bo
   p.chunk_w = static_cast<int>(std::min<int64_t>(n, CF_BLOCK));
   p.lanes_r = CF_BLOCK / p.chunk_w;
   const int64_t R = p.lanes_r;
-  const int64_t target = streaming ? STREAM_TILES : TARGET_TILES;
+  static const int64_t target_tiles = [] {  // tuning knob: SMC_TARGET_TILES overrides the default
+    const char* e = std::getenv("SMC_TARGET_TILES");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? static_cast<int64_t>(v) : TARGET_TILES;
+  }();
+  const int64_t target = streaming ? STREAM_TILES : target_tiles;
   int64_t want = (n_contracts * rows_local + target - 1) / target;
   if (streaming) want = std::max<int64_t>(want, (16384 + n - 1) / n);  // >= 16 Ki elements per tile
   want = std::max<int64_t>(want, 1);
