@@ -14,7 +14,10 @@ from ctypes import POINTER, Structure, byref, c_char_p, c_double, c_int, c_int64
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libspectralmc_b200.so")
+# SPECTRALMC_B200_LIB overrides the in-tree location (deployment); a path that does not exist is an error
+_LIB_PATH = os.environ.get("SPECTRALMC_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "lib", "libspectralmc_b200.so"
+)
 
 SMC_F32, SMC_F64 = 0, 1
 SMC_LOG_EULER, SMC_SIMPLE_EULER, SMC_LOG_EULER_STEPWISE = 0, 1, 2

@@ -67,3 +67,14 @@ def test_product_never_imports_the_oracle() -> None:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_missing_library_fails_loudly() -> None:
+    """No fallback: importing the package without the shared library is an ImportError."""
+    import subprocess
+    import sys
+
+    env = dict(os.environ, SPECTRALMC_B200_LIB="/nonexistent/libspectralmc_b200.so", PYTHONPATH=ROOT)
+    proc = subprocess.run([sys.executable, "-c", "import spectralmc_b200"], env=env, capture_output=True, text=True)
+    assert proc.returncode != 0
+    assert "ImportError" in proc.stderr and "no fallback" in proc.stderr

@@ -255,3 +255,36 @@ def test_paths_that_need_the_refinement_block() -> None:
         ogbm.simulate_paths_inplace(ref2, T, 1.0 / T, 100.0, 0.05, 0.0, 0.2, scheme != _cabi.SMC_SIMPLE_EULER)
         g2 = t2[0].cpu().numpy().astype(np.float64)
         assert np.max(np.abs(g2[cols] - ref2[-1][cols]) / ref2[-1][cols]) <= 2e-5
+
+
+def test_empty_contract_batch() -> None:
+    engine = _engine(Precision.float32, T=4, N=16, B=8)
+    out = expect_success(engine.cf_targets([]))
+    assert out.shape == (0, 16) and out.dtype == torch.complex64
+    assert expect_success(engine.snapshot()).sim_params.skip == 0
+
+
+def test_random_shapes_against_oracle() -> None:
+    """40 random (C, T, N, B, scheme, normalisation, dtype) draws, including N that are not powers of
+    two, N > 256, T not a multiple of 6, single rows — each against the oracle on the same counters."""
+    rng = np.random.default_rng(12345)
+    for trial in range(40):
+        C = int(rng.integers(1, 4))
+        T = int(rng.integers(1, 20))
+        N = int(rng.choice([1, 2, 3, 7, 16, 31, 32, 100, 128, 257, 300, 512]))
+        B = int(rng.integers(1, 40))
+        prec = "float32" if rng.random() < 0.5 else "float64"
+        scheme = "log_euler" if rng.random() < 0.6 else "simple_euler"
+        norm = "raw_paths" if rng.random() < 0.5 else "normalize_forwards"
+        rows = [(float(rng.uniform(1, 200)), float(rng.uniform(1, 200)), float(rng.uniform(0.05, 3)), float(rng.uniform(-0.1, 0.1)),
+                 float(rng.uniform(-0.1, 0.1)), float(rng.uniform(0.05, 0.8))) for _ in range(C)]
+        seed, first = int(rng.integers(1, 2**40)), int(rng.integers(0, 1000))
+        dtype = torch.float64 if prec == "float64" else torch.float32
+        ref = _oracle_cf(rows, T, N, B, np.dtype(prec), seed, first, scheme, norm)
+        got = _fused(rows, T, N, B, dtype, seed, first,
+                     _cabi.SMC_LOG_EULER if scheme == "log_euler" else _cabi.SMC_SIMPLE_EULER,
+                     _cabi.SMC_NORMALIZE if norm == "normalize_forwards" else _cabi.SMC_RAW)
+        tol = 1e-12 if prec == "float64" else 1e-5
+        for c in range(C):
+            scale = max(float(np.max(np.abs(ref[c]))), 1e-30)
+            assert float(np.max(np.abs(got[c] - ref[c]))) / scale <= tol or scale < 1e-9, (trial, C, T, N, B, prec, scheme, norm)
