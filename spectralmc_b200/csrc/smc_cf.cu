@@ -185,9 +185,14 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
     for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
   }
   const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
-  if (rem) {
-    float z[6];
-    normals6_f32_impl<REFINE>(col, nq, k_lo, k_hi, keys, z, min_word);
+  if (rem) {  // ragged last block: evaluate only the pairs that are consumed
+    float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (rem <= 2)
+      normals6_f32_impl<REFINE, 1>(col, nq, k_lo, k_hi, keys, z, min_word);
+    else if (rem <= 4)
+      normals6_f32_impl<REFINE, 2>(col, nq, k_lo, k_hi, keys, z, min_word);
+    else
+      normals6_f32_impl<REFINE, 3>(col, nq, k_lo, k_hi, keys, z, min_word);
 #pragma unroll
     for (int u = 0; u < 5; ++u)
       if (u < rem) consume<float, SCHEME>(acc, z[u], k);

@@ -139,7 +139,10 @@ static __device__ __noinline__ float3 refine_radius_uniforms(uint32_t col, uint3
 // its time loop and, in the 6e-5 of paths where some block needed the refinement, redo the path
 // with REFINE = true.  The result is identical to the specified stream; the hot loop loses the
 // compare/branch/reconvergence instructions (5 of 98 issue slots per block).
-template <bool REFINE>
+// NPAIRS < 3 evaluates only the first NPAIRS Box–Muller pairs (rows 6q .. 6q+2*NPAIRS-1): the
+// ragged last block of a path whose length is not a multiple of 6, and in particular the whole
+// path when timesteps <= 4 (the reference's own tests run timesteps = 1).
+template <bool REFINE, int NPAIRS = 3>
 __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                                   const PhiloxKeys& key, float (&z)[6], uint32_t& min_word) {
   uint32_t x[4];
@@ -155,14 +158,11 @@ __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint
       u[2] = f.z;
     }
   } else {
-    min_word = min(min(min_word, x[0]), min(x[1], x[2]));
+    min_word = min(min(min_word, x[0]), min(x[1], x[2]));  // unused pairs may only cause a needless exact redo
   }
-  const float a0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
-  const float a1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
-  const float a2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
-  box_muller_f32(u[0], a0, z[0], z[1]);
-  box_muller_f32(u[1], a1, z[2], z[3]);
-  box_muller_f32(u[2], a2, z[4], z[5]);
+  box_muller_f32(u[0], unit_float_21(__funnelshift_l(x[3], x[0], 12)), z[0], z[1]);
+  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12)), z[2], z[3]);
+  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12)), z[4], z[5]);
 }
 
 __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
