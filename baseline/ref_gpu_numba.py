@@ -20,7 +20,6 @@ import json
 import math
 import time
 
-import numpy as np
 import torch
 from numba import cuda
 

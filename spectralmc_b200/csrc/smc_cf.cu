@@ -171,7 +171,11 @@ __device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>
 
 // terminal price of global path `col` of the matrix (k_lo, k_hi): every one of the `timesteps`
 // normals is drawn and consumed.
-template <int SCHEME, bool REFINE>
+// RAGGED = false is the specialisation for timesteps % 6 == 0: the hot loop's throughput depends
+// on ptxas' interleaving of IMAD.WIDE / MUFU / LOP3 issue, and merely compiling the tail code into
+// the same kernel costs 2 % at config c2 (A/B in one run: 1.387 vs 1.414 ms), so kernels that
+// cannot have a tail do not contain one.
+template <int SCHEME, bool REFINE, bool RAGGED>
 __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi,
                                                    uint32_t& min_word) {
@@ -181,21 +185,30 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
   for (uint32_t q = 0; q < nq; ++q) {
     float z[6];
     normals6_f32_impl<REFINE>(col, q, k_lo, k_hi, keys, z, min_word);
+#ifndef SMC_SUM_TREE
+#define SMC_SUM_TREE 0
+#endif
+    if (SMC_SUM_TREE && SCHEME == SMC_LOG_EULER) {
+      acc += ((z[0] + z[1]) + (z[2] + z[3])) + (z[4] + z[5]);
+    } else {
 #pragma unroll
-    for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
+      for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
+    }
   }
-  const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
-  if (rem) {  // ragged last block: evaluate only the pairs that are consumed
-    float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (rem <= 2)
-      normals6_f32_impl<REFINE, 1>(col, nq, k_lo, k_hi, keys, z, min_word);
-    else if (rem <= 4)
-      normals6_f32_impl<REFINE, 2>(col, nq, k_lo, k_hi, keys, z, min_word);
-    else
-      normals6_f32_impl<REFINE, 3>(col, nq, k_lo, k_hi, keys, z, min_word);
+  if (RAGGED) {  // last block: evaluate only the pairs that are consumed
+    const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
+    if (rem) {
+      float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (rem <= 2)
+        normals6_f32_impl<REFINE, 1>(col, nq, k_lo, k_hi, keys, z, min_word);
+      else if (rem <= 4)
+        normals6_f32_impl<REFINE, 2>(col, nq, k_lo, k_hi, keys, z, min_word);
+      else
+        normals6_f32_impl<REFINE, 3>(col, nq, k_lo, k_hi, keys, z, min_word);
 #pragma unroll
-    for (int u = 0; u < 5; ++u)
-      if (u < rem) consume<float, SCHEME>(acc, z[u], k);
+      for (int u = 0; u < 5; ++u)
+        if (u < rem) consume<float, SCHEME>(acc, z[u], k);
+    }
   }
   if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
   return acc;
@@ -203,7 +216,7 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
 
 // the rare re-simulation (some block of the path had a zero radius field): same path with the
 // refinement applied.  Arguments by value so the caller keeps its key block in the constant bank.
-template <int SCHEME>
+template <int SCHEME, bool RAGGED>
 static __device__ __noinline__ float simulate_path_exact_f32(float X0, float lin0, float lin1, uint32_t col,
                                                              int64_t timesteps, uint32_t seed_lo, uint32_t seed_hi,
                                                              uint32_t k_lo, uint32_t k_hi) {
@@ -218,10 +231,10 @@ static __device__ __noinline__ float simulate_path_exact_f32(float X0, float lin
   k.lin0 = lin0;
   k.lin1 = lin1;
   uint32_t unused = 0;
-  return simulate_path_f32<SCHEME, true>(k, col, timesteps, keys, k_lo, k_hi, unused);
+  return simulate_path_f32<SCHEME, true, RAGGED>(k, col, timesteps, keys, k_lo, k_hi, unused);
 }
 
-template <int SCHEME>
+template <int SCHEME, bool RAGGED>
 __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
 #ifndef SMC_F32_POSTHOC_REFINE
@@ -229,16 +242,16 @@ __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, ui
 #endif
   uint32_t min_word = 0xffffffffu;
 #if SMC_F32_POSTHOC_REFINE
-  float v = simulate_path_f32<SCHEME, false>(k, col, timesteps, keys, k_lo, k_hi, min_word);
+  float v = simulate_path_f32<SCHEME, false, RAGGED>(k, col, timesteps, keys, k_lo, k_hi, min_word);
   if (__builtin_expect(min_word < 2048u, 0))
-    v = simulate_path_exact_f32<SCHEME>(k.X0, k.lin0, k.lin1, col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
+    v = simulate_path_exact_f32<SCHEME, RAGGED>(k.X0, k.lin0, k.lin1, col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
   return v;
 #else
-  return simulate_path_f32<SCHEME, true>(k, col, timesteps, keys, k_lo, k_hi, min_word);
+  return simulate_path_f32<SCHEME, true, RAGGED>(k, col, timesteps, keys, k_lo, k_hi, min_word);
 #endif
 }
 
-template <int SCHEME>
+template <int SCHEME, bool RAGGED>
 __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, uint32_t col, int64_t timesteps,
                                                     const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
   double acc = SCHEME == SMC_LOG_EULER ? 0.0 : k.X0;
@@ -267,11 +280,11 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 4  // 64 registers: measured best of {0 (72 regs), 4, 5, 6} at config c2 (1.387 ms vs 1.408-1.425)
+#define SMC_F32_FUSED_MIN_CTAS 5  // measured best of {3,4,5} x pair orders x sum forms (profiles/r1_codegen_variant_matrix.txt)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
-template <typename Real, int SRC, int SCHEME, int OUT>
+template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
 __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS))
     tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real)
         const int64_t path = row * p.n + col;  // global path index b*N + n (gbm_trainer.py:814-816)
         Real val;
         if (SRC == SRC_FUSED)
-          val = simulate_terminal<SCHEME>(k, static_cast<uint32_t>(path), p.timesteps, p.keys, k_lo, k_hi);
+          val = simulate_terminal<SCHEME, RAGGED>(k, static_cast<uint32_t>(path), p.timesteps, p.keys, k_lo, k_hi);
         else if (SRC == SRC_TERMINAL)
           val = __ldcs(static_cast<const Real*>(p.terminal_in) + local_base + path);
         else
@@ -556,12 +569,18 @@ static int launch_tile(TileParams p, int64_t contracts, int scheme, SimConsts<Re
   }
   const dim3 grid(static_cast<unsigned>(p.tiles), static_cast<unsigned>(std::min<int64_t>(contracts, 65535)),
                   static_cast<unsigned>((contracts + 65534) / 65535));
-  if (SRC != SRC_FUSED || scheme == SMC_LOG_EULER)
-    tile_kernel<Real, SRC, SMC_LOG_EULER, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
-  else if (scheme == SMC_SIMPLE_EULER)
-    tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
-  else
-    tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT><<<grid, CF_BLOCK, 0, st>>>(p);
+  // float32 fused kernels exist in two forms: with and without the ragged-tail code (see simulate_path_f32)
+  const bool whole_blocks = SRC == SRC_FUSED && sizeof(Real) == 4 && p.timesteps % 6 == 0;
+  if (SRC != SRC_FUSED || scheme == SMC_LOG_EULER) {
+    if (whole_blocks) tile_kernel<Real, SRC, SMC_LOG_EULER, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
+    else tile_kernel<Real, SRC, SMC_LOG_EULER, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
+  } else if (scheme == SMC_SIMPLE_EULER) {
+    if (whole_blocks) tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
+    else tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
+  } else {
+    if (whole_blocks) tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
+    else tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
+  }
   SMC_LAUNCH_OK("tile_kernel");
   return SMC_OK;
 }

@@ -160,9 +160,25 @@ __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint
   } else {
     min_word = min(min(min_word, x[0]), min(x[1], x[2]));  // unused pairs may only cause a needless exact redo
   }
+#ifndef SMC_BM_ORDER
+#define SMC_BM_ORDER 2  // evaluation order of the pairs: a pure scheduling hint for ptxas (results identical)
+#endif
+#if SMC_BM_ORDER == 0
   box_muller_f32(u[0], unit_float_21(__funnelshift_l(x[3], x[0], 12)), z[0], z[1]);
   if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12)), z[2], z[3]);
   if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12)), z[4], z[5]);
+#elif SMC_BM_ORDER == 1
+  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12)), z[4], z[5]);
+  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12)), z[2], z[3]);
+  box_muller_f32(u[0], unit_float_21(__funnelshift_l(x[3], x[0], 12)), z[0], z[1]);
+#else
+  const float a0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
+  const float a1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
+  const float a2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
+  box_muller_f32(u[0], a0, z[0], z[1]);
+  if (NPAIRS >= 2) box_muller_f32(u[1], a1, z[2], z[3]);
+  if (NPAIRS >= 3) box_muller_f32(u[2], a2, z[4], z[5]);
+#endif
 }
 
 __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,

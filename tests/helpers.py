@@ -14,8 +14,8 @@ from spectralmc_b200.gbm import (
     build_simulation_params,
 )
 from spectralmc_b200.numerical import Precision
-from spectralmc_b200.result import Failure, Result, Success
-from spectralmc_b200.sobol_sampler import BoundSpec, DomainBounds, build_bound_spec, build_domain_bounds
+from spectralmc_b200.result import Failure, Success
+from spectralmc_b200.sobol_sampler import DomainBounds, build_bound_spec, build_domain_bounds
 
 
 def expect_success(result):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise `-Xptxas -v` logs: registers, spills, shared memory per kernel."""
-import re, subprocess, sys, glob, os
+import re, subprocess, glob, os
 here = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spectralmc_b200", "csrc")
 for f in sorted(glob.glob(os.path.join(here, "*.ptxas.log"))):
     txt = open(f).read()
