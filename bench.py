@@ -45,7 +45,7 @@ WORKLOADS = {
     "c4": dict(contracts=512, T=365, N=256, B=4096, dtype="float64"),
 }
 # SASS-counted work per fp32 path-step of the fused log-Euler kernel (profiles/ has the listing):
-ISSUE_SLOTS_PER_STEP = 15.33  # warp-instructions issued per path-step per lane (92 per 6-normal block, SASS)
+ISSUE_SLOTS_PER_STEP = 15.08  # warp-instructions issued per path-step per lane (181 per two 6-normal blocks, SASS)
 XU_OPS_PER_STEP = 2.0  # (LG2 + SQRT + SIN + COS) per Box–Muller pair / 2 normals; log-sum variant
 
 

@@ -181,7 +181,11 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
                                                    uint32_t& min_word) {
   float acc = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
   const uint32_t nq = static_cast<uint32_t>(timesteps / 6);
-#pragma unroll 1  // unroll 2 costs registers: under a 5-CTA cap ptxas rematerialises and the loop grows 18 %
+#ifndef SMC_F32_UNROLL
+#define SMC_F32_UNROLL 2  // codegen knob, see profiles/r1_codegen_variant_matrix.txt
+#endif
+  constexpr int kUnroll = SMC_F32_UNROLL;
+#pragma unroll kUnroll
   for (uint32_t q = 0; q < nq; ++q) {
     float z[6];
     normals6_f32_impl<REFINE>(col, q, k_lo, k_hi, keys, z, min_word);
@@ -280,7 +284,7 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 5  // measured best of {3,4,5} x pair orders x sum forms (profiles/r1_codegen_variant_matrix.txt)
+#define SMC_F32_FUSED_MIN_CTAS 4  // with SMC_F32_UNROLL=2, SMC_BM_ORDER=2: measured best (profiles/r1_codegen_variant_matrix.txt)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
