@@ -288,3 +288,22 @@ def test_random_shapes_against_oracle() -> None:
         for c in range(C):
             scale = max(float(np.max(np.abs(ref[c]))), 1e-30)
             assert float(np.max(np.abs(got[c] - ref[c]))) / scale <= tol or scale < 1e-9, (trial, C, T, N, B, prec, scheme, norm)
+
+
+def test_baseline_config_c4_against_black76() -> None:
+    """BASELINE.json configs[3] at full size: float64, 512 Sobol contracts (seed 31, as
+    tests/test_gbm.py:110 of the reference), 365 timesteps, network_size 256, B = 4096 — 1.96e11
+    path-steps per repetition.  8 repetitions; acceptance as the reference's (<= 5 % of contracts
+    beyond 3 standard errors of the analytic price, RMSPE <= 0.15 where the price is >= 1)."""
+    rows = sobol_contracts(512, seed=31)
+    engine = _engine(Precision.float64, T=365, N=256, B=4096, seed=7)
+    dev_rows = torch.tensor(rows, device="cuda")
+    vals = np.stack([expect_success(engine.cf_targets(dev_rows))[:, 0].real.cpu().numpy() / 256 for _ in range(8)])
+    mean, sd = vals.mean(axis=0), vals.std(axis=0, ddof=1)
+    analytic = np.array([black76(*r)["put_price"] for r in rows])
+    se = sd / math.sqrt(vals.shape[0])
+    z = np.where(se > 0, np.abs(mean - analytic) / np.where(se > 0, se, 1.0), np.where(np.abs(mean - analytic) <= 1e-8 * np.maximum(analytic, 1), 0.0, 4.0))
+    big = analytic >= 1.0
+    assert float(np.mean(z > 3.0)) <= 0.05, np.sort(z)[-8:]
+    assert float(np.sqrt(np.mean(((mean - analytic) / analytic)[big] ** 2))) <= 0.15
+    assert expect_success(engine.snapshot()).sim_params.skip == 8 * 512
