@@ -129,6 +129,14 @@ size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t network_size, in
 int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t network_size, int dtype, int method,
                     void* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Per-row spectra WITHOUT the batch mean — replaces cp.fft.fft(tensor, axis=-1) of the ComputeFFT
+ * effect (effects/interpreter.py:680-712) for a real (B, N) matrix; `out` is (B, N) complex of
+ * matching width.  Powers of two in [32, 512] use the register/shuffle FFT of SMC_CF_ROW_FFT;
+ * any other N <= 8192 a table-driven DFT (O(N^2) per row).  The training path never needs this
+ * (it consumes the batch mean, smc_cf_fft_mean). */
+int smc_fft_rows(const void* mat, int64_t batches, int64_t network_size, int dtype, void* out,
+                 void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fused batch path — replaces the whole per-contract Python loop
  *     [ _simulate_fft(c) for c in sobol_inputs ]  +  cp.asarray(fft_values)

@@ -27,7 +27,7 @@ SMC_CF_MEAN_THEN_FFT, SMC_CF_ROW_FFT = 0, 1
 EXPORTS = (
     "smc_version smc_last_error smc_device_info smc_philox_normals smc_gbm_paths_inplace "
     "smc_gbm_terminal_from_normals smc_normalize_rows_workspace_bytes smc_normalize_rows smc_payoff "
-    "smc_means3_workspace_bytes smc_means3 smc_cf_fft_mean_workspace_bytes smc_cf_fft_mean "
+    "smc_means3_workspace_bytes smc_means3 smc_cf_fft_mean_workspace_bytes smc_cf_fft_mean smc_fft_rows "
     "smc_cf_fused_workspace_bytes smc_cf_fused_launch_count smc_cf_fused smc_fused_terminal_workspace_bytes smc_fused_terminal "
     "smc_cf_from_terminal_workspace_bytes smc_cf_from_terminal smc_cf_fused_host_workspace_bytes "
     "smc_cf_fused_host smc_pipe_calibrate"
@@ -97,6 +97,7 @@ def _load() -> ctypes.CDLL:
     lib.smc_payoff.argtypes = [c_void_p, c_int64, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p]
     lib.smc_means3.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cf_fft_mean.argtypes = [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_fft_rows.argtypes = [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]
     lib.smc_cf_fused.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_fused_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cf_from_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
@@ -240,6 +241,15 @@ def cf_fft_mean(mat: torch.Tensor, method: int = SMC_CF_MEAN_THEN_FFT) -> torch.
             mat.data_ptr(), B, N, dtype_code(mat.dtype), method, out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()
         )
     )
+    return out
+
+
+def fft_rows(mat: torch.Tensor) -> torch.Tensor:
+    """Forward DFT of every row of a real (B, N) matrix -> (B, N) complex (no batch mean)."""
+    _require_cuda(mat, "mat")
+    B, N = mat.shape
+    out = torch.empty((B, N), dtype=complex_dtype(mat.dtype), device=mat.device)
+    check(LIB.smc_fft_rows(mat.data_ptr(), B, N, dtype_code(mat.dtype), out.data_ptr(), _stream()))
     return out
 
 

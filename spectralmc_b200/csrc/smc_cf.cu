@@ -885,6 +885,15 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   return reduce_and_finalize<double>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
 }
 
+// ---- per-row spectra (the ComputeFFT operator) ----------------------------------------------
+extern "C" int smc_fft_rows(const void* mat, int64_t batches, int64_t n, int dtype, void* out, void* stream) {
+  clear_error();
+  SMC_REQUIRE(batches > 0 && n > 0, "smc_fft_rows: invalid shape (%lld, %lld)", (long long)batches, (long long)n);
+  SMC_REQUIRE(mat && out, "smc_fft_rows: NULL pointer");
+  SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_fft_rows: invalid dtype %d", dtype);
+  return fft_rows(mat, batches, n, dtype, out, as_stream(stream));
+}
+
 // ---- host-buffer entry point ----------------------------------------------------------------
 extern "C" size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* a) {
   if (a == nullptr || a->n_contracts <= 0) return 0;

@@ -27,6 +27,7 @@ int sm_count();
 // SMC_CF_ROW_FFT (smc_rowfft.cu)
 bool rowfft_supported(int64_t n);
 size_t rowfft_workspace_bytes(int64_t batches, int64_t n);
+int fft_rows(const void* mat, int64_t batches, int64_t n, int dtype, void* out, cudaStream_t st);
 int rowfft_mean(const void* mat, int64_t batches, int64_t n, int dtype, void* out, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 

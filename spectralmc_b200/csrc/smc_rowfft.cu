@@ -37,10 +37,13 @@ __device__ __forceinline__ Real shfl_xor(Real v, int mask) {
   return __shfl_xor_sync(0xffffffffu, v, mask);
 }
 
-template <typename Real, int E>
+// STORE_ROWS = true writes every row's spectrum to `spectra` [batches, N, 2] in natural order
+// instead of accumulating the batch mean (smc_fft_rows, the ComputeFFT operator).
+template <typename Real, int E, bool STORE_ROWS = false>
 __global__ void __launch_bounds__(RF_BLOCK)
     rowfft_mean_kernel(const Real* __restrict__ mat, int64_t batches, int64_t rows_per_cta,
-                       double* __restrict__ partial /* [ctas, N, 2] bit-reversed order */) {
+                       double* __restrict__ partial /* [ctas, N, 2] bit-reversed order */,
+                       Real* __restrict__ spectra = nullptr) {
   constexpr int N = 32 * E;
   __shared__ Real tw_re[N / 2], tw_im[N / 2];
   __shared__ double red[RF_WARPS][32 * 2];
@@ -113,12 +116,24 @@ __global__ void __launch_bounds__(RF_BLOCK)
         }
       }
     }
+    if (STORE_ROWS) {
+      constexpr int LOG2N = 5 + (E == 1 ? 0 : E == 2 ? 1 : E == 4 ? 2 : E == 8 ? 3 : 4);
+      Real* dst = spectra + row * N * 2;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const unsigned k = __brev(static_cast<unsigned>(e * 32 + lane)) >> (32 - LOG2N);  // position holds X[bitrev]
+        dst[2 * k] = xr[e];
+        dst[2 * k + 1] = xi[e];
+      }
+      continue;
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       acc_re[e] += static_cast<double>(xr[e]);
       acc_im[e] += static_cast<double>(xi[e]);
     }
   }
+  if (STORE_ROWS) return;
   // CTA fold over warps (fixed order), one element slot e at a time
   double* out = partial + static_cast<int64_t>(blockIdx.x) * N * 2;
 #pragma unroll
@@ -153,6 +168,37 @@ __global__ void __launch_bounds__(RF_BLOCK)
     const unsigned k = __brev(static_cast<unsigned>(j)) >> (32 - log2n);
     out[2 * k] = static_cast<Real>(sr * scale);
     out[2 * k + 1] = static_cast<Real>(si * scale);
+  }
+}
+
+// any N <= 8192: one CTA per row, table-driven DFT in float64 shared memory (O(N^2) per row)
+template <typename Real>
+__global__ void __launch_bounds__(RF_BLOCK)
+    dft_rows_kernel(const Real* __restrict__ mat, int64_t n, Real* __restrict__ spectra) {
+  extern __shared__ double dsm[];
+  double* x = dsm;
+  double* twr = dsm + n;
+  double* twi = twr + n;
+  const int64_t row = blockIdx.x;
+  for (int64_t j = threadIdx.x; j < n; j += RF_BLOCK) {
+    double s, c;
+    sincospi(-2.0 * static_cast<double>(j) / static_cast<double>(n), &s, &c);
+    twr[j] = c;
+    twi[j] = s;
+    x[j] = static_cast<double>(mat[row * n + j]);
+  }
+  __syncthreads();
+  for (int64_t k = threadIdx.x; k < n; k += RF_BLOCK) {
+    double re = 0.0, im = 0.0;
+    int64_t m = 0;
+    for (int64_t j = 0; j < n; ++j) {
+      re = fma(x[j], twr[m], re);
+      im = fma(x[j], twi[m], im);
+      m += k;
+      if (m >= n) m -= n;
+    }
+    spectra[(row * n + k) * 2] = static_cast<Real>(re);
+    spectra[(row * n + k) * 2 + 1] = static_cast<Real>(im);
   }
 }
 
@@ -193,6 +239,36 @@ static int rowfft_launch(const Real* mat, int64_t batches, int64_t n, Real* out,
                                                       1.0 / static_cast<double>(batches), out);
   SMC_LAUNCH_OK("rowfft_finalize_kernel");
   return SMC_OK;
+}
+
+template <typename Real>
+static int fft_rows_launch(const Real* mat, int64_t batches, int64_t n, Real* out, cudaStream_t st) {
+  if (rowfft_supported(n)) {
+    const RowFftPlan p = rowfft_plan(batches);
+    const unsigned grid = static_cast<unsigned>(p.ctas);
+    switch (n) {
+      case 32: rowfft_mean_kernel<Real, 1, true><<<grid, RF_BLOCK, 0, st>>>(mat, batches, p.rows_per_cta, nullptr, out); break;
+      case 64: rowfft_mean_kernel<Real, 2, true><<<grid, RF_BLOCK, 0, st>>>(mat, batches, p.rows_per_cta, nullptr, out); break;
+      case 128: rowfft_mean_kernel<Real, 4, true><<<grid, RF_BLOCK, 0, st>>>(mat, batches, p.rows_per_cta, nullptr, out); break;
+      case 256: rowfft_mean_kernel<Real, 8, true><<<grid, RF_BLOCK, 0, st>>>(mat, batches, p.rows_per_cta, nullptr, out); break;
+      default: rowfft_mean_kernel<Real, 16, true><<<grid, RF_BLOCK, 0, st>>>(mat, batches, p.rows_per_cta, nullptr, out); break;
+    }
+    SMC_LAUNCH_OK("rowfft kernel (store)");
+    return SMC_OK;
+  }
+  if (n > 8192) return set_error(SMC_EUNSUPPORTED, "smc_fft_rows: network_size %lld > 8192 is not supported", (long long)n);
+  if (batches > 0x7fffffffLL) return set_error(SMC_EINVAL, "smc_fft_rows: too many rows");
+  const size_t smem = static_cast<size_t>(n) * 24;
+  if (smem > 48 * 1024)
+    SMC_CUDA_OK(cudaFuncSetAttribute(dft_rows_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dft_rows_kernel<Real><<<static_cast<unsigned>(batches), RF_BLOCK, smem, st>>>(mat, n, out);
+  SMC_LAUNCH_OK("dft_rows_kernel");
+  return SMC_OK;
+}
+
+int fft_rows(const void* mat, int64_t batches, int64_t n, int dtype, void* out, cudaStream_t st) {
+  if (dtype == SMC_F32) return fft_rows_launch<float>(static_cast<const float*>(mat), batches, n, static_cast<float*>(out), st);
+  return fft_rows_launch<double>(static_cast<const double*>(mat), batches, n, static_cast<double*>(out), st);
 }
 
 int rowfft_mean(const void* mat, int64_t batches, int64_t n, int dtype, void* out, void* ws, size_t ws_bytes,

@@ -9,10 +9,11 @@ over a name -> tensor registry (the role of ``SharedRegistry.register_tensor/get
   counter-based stream, which is what the engine's ``skip`` means, gbm.py:372-380);
 * ``SimulatePaths``    -> copy of the normals (:623) + ``smc_gbm_paths_inplace`` (256 threads per
   block, :626) + ``smc_normalize_rows`` when normalisation is requested (:660-665);
-* ``ComputeFFT``       -> forward DFT along ``axis`` (:703).  This operator returns the FULL
-  per-row spectrum, which the training path never needs (it consumes the batch MEAN,
-  gbm_trainer.py:814-817 -> ``smc_cf_fft_mean``); it is served by ``torch.fft.fft`` and is not part
-  of the measured hot path.
+* ``ComputeFFT``       -> forward DFT along ``axis`` (:703): ``smc_fft_rows`` for a real 2-D tensor
+  transformed along its last axis with ``N <= 8192`` (every case the Monte-Carlo path produces).
+  This operator returns the FULL per-row spectrum, which the training path never needs (it
+  consumes the batch MEAN, gbm_trainer.py:814-817 -> ``smc_cf_fft_mean``).  Other ranks / axes /
+  complex inputs are outside the path and are rejected with a ``MonteCarloError``.
 
 Unlike the reference interpreter, which is float32-only (:583), the dtype is a constructor
 argument.  ``interpret`` is ``async`` like the reference's; ``run`` is the synchronous form.
@@ -118,4 +119,8 @@ class MonteCarloOperators:
         got = self._registry.get_tensor(effect.input_tensor_id)
         if isinstance(got, Failure):
             return Failure(MonteCarloError(message=f"Tensor not found: {effect.input_tensor_id}"))
-        return self._store(effect.output_tensor_id, torch.fft.fft(got.value, dim=effect.axis))
+        t = got.value
+        axis = effect.axis if effect.axis >= 0 else t.dim() + effect.axis
+        if t.dim() != 2 or axis != 1 or t.is_complex():
+            return Failure(MonteCarloError(message="ComputeFFT supports a real 2-D tensor transformed along its last axis"))
+        return self._store(effect.output_tensor_id, _cabi.fft_rows(t.contiguous()))

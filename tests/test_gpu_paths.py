@@ -159,6 +159,18 @@ def test_cf_row_fft_on_reference_payoffs() -> None:
     assert rel_max(got, ref) <= 2e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("b,n", [(1, 32), (9, 64), (300, 128), (17, 512), (5, 1), (7, 12), (33, 100), (3, 1024), (2, 8192)])
+def test_fft_rows(dtype, b, n) -> None:
+    """smc_fft_rows == numpy.fft.fft(mat, axis=1) (shuffle FFT for 32..512 powers of two, table DFT otherwise)."""
+    mat = (np.random.default_rng(b * 7 + n).random((b, n)) * 3).astype(np.float32 if dtype == torch.float32 else np.float64)
+    got = _cabi.fft_rows(torch.from_numpy(mat).cuda()).cpu().numpy()
+    ref = np.fft.fft(mat.astype(np.float64), axis=1)
+    assert got.shape == (b, n) and rel_max(got, ref) <= (2e-6 if dtype == torch.float32 else 1e-13)
+    with pytest.raises(_cabi.SmcError, match="8192"):
+        _cabi.fft_rows(torch.zeros((1, 9000), device="cuda"))
+
+
 def test_cf_large_network_size_fallback() -> None:
     mat = np.random.default_rng(0).random((2, 9000))
     cf = _cabi.cf_fft_mean(torch.from_numpy(mat).cuda()).cpu().numpy()
