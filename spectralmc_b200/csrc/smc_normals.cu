@@ -39,8 +39,14 @@ struct StoreVec<4> {
 // grid.x covers column groups, grid.y covers runs of `groups_per_cta` row groups.  Full 6-row
 // groups take the unguarded fast path (pointer bumped by `cols` per row); only the last group of a
 // matrix whose row count is not a multiple of 6 checks rows.
+#ifndef SMC_NORMALS_MIN_CTAS
+#define SMC_NORMALS_MIN_CTAS 3  // measured best of {3,4,5,6} x run lengths: 5.9 TB/s (profiles/r1_codegen_variant_matrix.txt)
+#endif
+#ifndef SMC_NORMALS_MAX_GROUPS
+#define SMC_NORMALS_MAX_GROUPS 42
+#endif
 template <int VEC>
-__global__ void __launch_bounds__(NORMALS_BLOCK, 4)
+__global__ void __launch_bounds__(NORMALS_BLOCK, SMC_NORMALS_MIN_CTAS)
     philox_normals_f32_kernel(float* __restrict__ out, int64_t rows, int64_t cols, PhiloxKeys key,
                               uint32_t k_lo, uint32_t k_hi, int groups_per_cta) {
   const int64_t col0 = (static_cast<int64_t>(blockIdx.x) * NORMALS_BLOCK + threadIdx.x) * VEC;
@@ -140,7 +146,7 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
     // enough CTAs along y to fill the machine for narrow matrices, long runs for wide ones
     const int64_t col_ctas = (cols / v + NORMALS_BLOCK - 1) / NORMALS_BLOCK;
     int groups_per_cta = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nq, (col_ctas * nq + 4735) / 4736)));
-    groups_per_cta = std::min(groups_per_cta, 8);
+    groups_per_cta = std::min(groups_per_cta, SMC_NORMALS_MAX_GROUPS);
     const int64_t gy = (nq + groups_per_cta - 1) / groups_per_cta;
     SMC_REQUIRE(gy <= 65535, "smc_philox_normals: too many rows (%lld) for one launch", (long long)rows);
     dim3 grid(static_cast<unsigned>(col_ctas), static_cast<unsigned>(gy));

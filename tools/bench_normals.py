@@ -12,4 +12,4 @@ for dtype, cols in ((torch.float32, 128 * 16384), (torch.float64, 128 * 8192)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); _cabi.philox_normals(z, 7, 1); b.record(); b.synchronize()
         best = min(best, a.elapsed_time(b))
-    print(json.dumps({"vec": os.environ.get("SMC_NORMALS_VEC", "default"), "dtype": str(dtype), "ms": best, "GBps": z.numel() * z.element_size() / best / 1e6}))
+    print(json.dumps({"lib": os.environ.get("SMC_LIB", "default"), "vec": os.environ.get("SMC_NORMALS_VEC", "default"), "dtype": str(dtype), "ms": best, "GBps": z.numel() * z.element_size() / best / 1e6}))
