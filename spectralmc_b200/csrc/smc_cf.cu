@@ -283,13 +283,16 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #ifndef SMC_F64_FUSED_MIN_CTAS
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
+#ifndef SMC_F32_FUSED_MIN_CTAS_OTHER
+#define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
+#endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
 #define SMC_F32_FUSED_MIN_CTAS 4  // with SMC_F32_UNROLL=2, SMC_BM_ORDER=2: measured best (profiles/r1_codegen_variant_matrix.txt)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
 template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
-__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS))
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : ((SCHEME == SMC_LOG_EULER && OUT == OUT_COLSUM) ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_OTHER)))
     tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
   const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
