@@ -21,7 +21,13 @@
 
 namespace smc {
 
-constexpr int PATH_UNROLL = 8;
+#ifndef SMC_PATH_UNROLL
+#define SMC_PATH_UNROLL 8
+#endif
+#ifndef SMC_PATH_STREAM_STORE
+#define SMC_PATH_STREAM_STORE 1  // st.global.cs: +1 % on the in-place kernel (6.1 vs 6.05 TB/s)
+#endif
+constexpr int PATH_UNROLL = SMC_PATH_UNROLL;
 
 struct PathConsts {
   double X0;
@@ -127,7 +133,10 @@ __global__ void __launch_bounds__(1024) gbm_paths_kernel(Real* __restrict__ io, 
           }
           if (STORE_PATHS) zv[v] = outv;
         }
-        if (STORE_PATHS) *reinterpret_cast<P*>(io + (i0 + u) * cols + col0) = buf[u];
+        if (STORE_PATHS) {
+          if (SMC_PATH_STREAM_STORE) __stcs(reinterpret_cast<P*>(io + (i0 + u) * cols + col0), buf[u]);
+          else *reinterpret_cast<P*>(io + (i0 + u) * cols + col0) = buf[u];
+        }
       }
     }
   }
