@@ -198,6 +198,70 @@ size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* args);
 int smc_cf_fused_host(const smc_fused_args* args, const double* contracts_host, void* cf_host,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * CVNN step — the consumer of the [C, N] targets.  Replaces, for networks
+ * that are a (possibly nested) ComplexSequential of ComplexLinear / modReLU / zReLU
+ * (cvnn.py:65-146, 149-162, 168-210, 439-452), the op-by-op torch execution of
+ *     GbmCVNNPricer._torch_step (gbm_trainer.py:819-835):
+ *         pred = cvnn(real_in, imag_in)
+ *         loss = mse(pred_r, Re targets) + mse(pred_i, Im targets)
+ *         zero_grad(); loss.backward(); adam.step()         (optim.Adam, gbm_trainer.py:1513)
+ * and the forward of predict_price (gbm_trainer.py:1722-1728), with a fixed sequence of
+ * stream-ordered launches that never touches the host (CUDA-graph capturable; the Adam step
+ * counter lives on the device).  ComplexLinear is ONE complex GEMM with the bias and the
+ * following activation fused into its epilogue.  Unsupported layers (the batch norms, residual
+ * wrappers) are reported by the caller not building a descriptor — those networks stay on torch.
+ *
+ * Parameters live in ONE flat buffer of the network dtype; each layer's block starts at
+ * `param_offset` (elements) and is laid out in the order of torch's module.parameters():
+ *     LINEAR : real_weight[out, in], imag_weight[out, in] (, real_bias[out], imag_bias[out])
+ *     MODRELU: bias[features]            ZRELU: nothing
+ * `grads`, `exp_avg`, `exp_avg_sq` are flat buffers of the same length and layout.
+ * Activations are row-major planes (real, imag) of shape [rows, features]; `targets` is
+ * [rows, out] interleaved complex of the network dtype.  `loss` is a DEVICE double.
+ */
+enum smc_cvnn_layer_kind { SMC_LAYER_LINEAR = 0, SMC_LAYER_MODRELU = 1, SMC_LAYER_ZRELU = 2 };
+
+typedef struct smc_cvnn_layer {
+  int kind;
+  int has_bias;          /* LINEAR only                                                      */
+  int64_t in_features;   /* LINEAR: inputs; MODRELU: features                                */
+  int64_t out_features;  /* LINEAR only                                                      */
+  int64_t param_offset;  /* first element of this layer's parameters in the flat buffer     */
+} smc_cvnn_layer;
+
+typedef struct smc_cvnn_net {
+  const smc_cvnn_layer* layers; /* host array, flattened in execution order                  */
+  int n_layers;
+  int dtype;
+  int64_t n_inputs;             /* width of (real_in, imag_in)                               */
+  int64_t n_params;             /* length of the flat parameter buffer                       */
+} smc_cvnn_net;
+
+/* torch.optim.Adam hyper-parameters (no weight decay, no amsgrad — the trainer's defaults) */
+typedef struct smc_adam_args {
+  double lr, beta1, beta2, eps;
+} smc_adam_args;
+
+size_t smc_cvnn_workspace_bytes(const smc_cvnn_net* net, int64_t rows, int training);
+/* width of the network output, or -1 if the descriptor is inconsistent */
+int64_t smc_cvnn_output_width(const smc_cvnn_net* net);
+int smc_cvnn_forward(const smc_cvnn_net* net, const void* params, const void* in_r, const void* in_i,
+                     int64_t rows, void* out_r, void* out_i, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* forward + loss + backward: writes every element of `grads` and the scalar *loss */
+int smc_cvnn_loss_backward(const smc_cvnn_net* net, const void* params, const void* in_r,
+                           const void* in_i, const void* targets, int64_t rows, void* grads,
+                           double* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* one Adam update of n elements; *step (device int64, steps taken so far) is incremented */
+int smc_adam_step(void* params, const void* grads, void* exp_avg, void* exp_avg_sq, int64_t n,
+                  int dtype, int64_t* step, const smc_adam_args* hyper, void* stream);
+/* smc_cvnn_loss_backward followed by smc_adam_step over the whole parameter buffer */
+int smc_cvnn_train_step(const smc_cvnn_net* net, void* params, void* grads, void* exp_avg,
+                        void* exp_avg_sq, int64_t* step, const smc_adam_args* hyper, const void* in_r,
+                        const void* in_i, const void* targets, int64_t rows, double* loss,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Pipe-peak calibration microbenchmarks (FP32 FMA issue and MUFU/XU), used by bench.py to
  * state the compute roofline on the box it runs on: each runs `iters` dependent-chain
  * iterations per thread on a full grid and returns executed lane-operations in *ops.

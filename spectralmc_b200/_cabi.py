@@ -23,6 +23,7 @@ SMC_F32, SMC_F64 = 0, 1
 SMC_LOG_EULER, SMC_SIMPLE_EULER, SMC_LOG_EULER_STEPWISE = 0, 1, 2
 SMC_NORMALIZE, SMC_RAW = 0, 1
 SMC_CF_MEAN_THEN_FFT, SMC_CF_ROW_FFT = 0, 1
+SMC_EINVAL = 1
 
 EXPORTS = (
     "smc_version smc_last_error smc_device_info smc_philox_normals smc_gbm_paths_inplace "
@@ -30,8 +31,12 @@ EXPORTS = (
     "smc_means3_workspace_bytes smc_means3 smc_cf_fft_mean_workspace_bytes smc_cf_fft_mean smc_fft_rows "
     "smc_cf_fused_workspace_bytes smc_cf_fused_launch_count smc_cf_fused smc_fused_terminal_workspace_bytes smc_fused_terminal "
     "smc_cf_from_terminal_workspace_bytes smc_cf_from_terminal smc_cf_fused_host_workspace_bytes "
-    "smc_cf_fused_host smc_pipe_calibrate"
+    "smc_cf_fused_host smc_pipe_calibrate "
+    "smc_cvnn_workspace_bytes smc_cvnn_output_width smc_cvnn_forward smc_cvnn_loss_backward smc_adam_step "
+    "smc_cvnn_train_step"
 ).split()
+
+SMC_LAYER_LINEAR, SMC_LAYER_MODRELU, SMC_LAYER_ZRELU = 0, 1, 2
 
 
 class SmcError(RuntimeError):
@@ -60,6 +65,36 @@ class FusedArgs(Structure):
         ("seed", c_uint64),
         ("first_matrix_index", c_uint64),
     ]
+
+
+class CvnnLayer(Structure):
+    """``smc_cvnn_layer`` (include/spectralmc_b200.h)."""
+
+    _fields_ = [
+        ("kind", c_int),
+        ("has_bias", c_int),
+        ("in_features", c_int64),
+        ("out_features", c_int64),
+        ("param_offset", c_int64),
+    ]
+
+
+class CvnnNet(Structure):
+    """``smc_cvnn_net``."""
+
+    _fields_ = [
+        ("layers", POINTER(CvnnLayer)),
+        ("n_layers", c_int),
+        ("dtype", c_int),
+        ("n_inputs", c_int64),
+        ("n_params", c_int64),
+    ]
+
+
+class AdamArgs(Structure):
+    """``smc_adam_args``."""
+
+    _fields_ = [("lr", c_double), ("beta1", c_double), ("beta2", c_double), ("eps", c_double)]
 
 
 def _load() -> ctypes.CDLL:
@@ -103,6 +138,17 @@ def _load() -> ctypes.CDLL:
     lib.smc_cf_from_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cf_fused_host.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_pipe_calibrate.argtypes = [c_int, c_int64, POINTER(c_double), c_void_p, c_void_p]
+    lib.smc_cvnn_workspace_bytes.argtypes = [POINTER(CvnnNet), c_int64, c_int]
+    lib.smc_cvnn_output_width.argtypes = [POINTER(CvnnNet)]
+    lib.smc_cvnn_output_width.restype = c_int64
+    lib.smc_cvnn_forward.argtypes = [POINTER(CvnnNet)] + [c_void_p] * 3 + [c_int64] + [c_void_p] * 3 + [c_size_t, c_void_p]
+    lib.smc_cvnn_loss_backward.argtypes = (
+        [POINTER(CvnnNet)] + [c_void_p] * 4 + [c_int64] + [c_void_p] * 3 + [c_size_t, c_void_p]
+    )
+    lib.smc_adam_step.argtypes = [c_void_p] * 4 + [c_int64, c_int, c_void_p, POINTER(AdamArgs), c_void_p]
+    lib.smc_cvnn_train_step.argtypes = (
+        [POINTER(CvnnNet)] + [c_void_p] * 5 + [POINTER(AdamArgs)] + [c_void_p] * 3 + [c_int64] + [c_void_p] * 2 + [c_size_t, c_void_p]
+    )
     return lib
 
 
@@ -340,3 +386,94 @@ def pipe_calibrate(kind: int, iters: int, device: torch.device) -> tuple[float, 
     stop.record()
     stop.synchronize()
     return ops.value, start.elapsed_time(stop)
+
+
+# --------------------------------------------------------------------------- CVNN step
+def make_cvnn_net(layers: list[tuple], n_inputs: int, dtype: torch.dtype) -> tuple[CvnnNet, int]:
+    """Descriptor for ``layers`` = [("linear", in, out, bias) | ("modrelu", features) | ("zrelu",)].
+
+    Parameter offsets follow ``module.parameters()`` order with no padding; returns the descriptor
+    and the flat parameter count.  The layer array is kept alive as ``net._keep``.
+    """
+    arr = (CvnnLayer * len(layers))()
+    offset = 0
+    for slot, layer in zip(arr, layers):
+        kind = layer[0]
+        slot.param_offset = offset
+        if kind == "linear":
+            slot.kind, slot.in_features, slot.out_features, slot.has_bias = SMC_LAYER_LINEAR, layer[1], layer[2], int(layer[3])
+            offset += 2 * layer[1] * layer[2] + (2 * layer[2] if layer[3] else 0)
+        elif kind == "modrelu":
+            slot.kind, slot.in_features = SMC_LAYER_MODRELU, layer[1]
+            offset += layer[1]
+        elif kind == "zrelu":
+            slot.kind = SMC_LAYER_ZRELU
+        else:
+            raise ValueError(f"unsupported CVNN layer {kind!r}")
+    net = CvnnNet(arr, len(layers), dtype_code(dtype), n_inputs, offset)
+    net._keep = arr
+    return net, offset
+
+
+def cvnn_workspace_bytes(net: CvnnNet, rows: int, training: bool) -> int:
+    n = int(LIB.smc_cvnn_workspace_bytes(byref(net), rows, int(training)))
+    if n == 0:
+        raise SmcError(SMC_EINVAL, LIB.smc_last_error().decode() or "inconsistent CVNN descriptor")
+    return n
+
+
+def cvnn_output_width(net: CvnnNet) -> int:
+    w = int(LIB.smc_cvnn_output_width(byref(net)))
+    if w < 0:
+        raise SmcError(SMC_EINVAL, LIB.smc_last_error().decode())
+    return w
+
+
+def cvnn_forward(net: CvnnNet, params: torch.Tensor, in_r: torch.Tensor, in_i: torch.Tensor, out_r: torch.Tensor,
+                 out_i: torch.Tensor, workspace: torch.Tensor) -> None:
+    for t, n in ((params, "params"), (in_r, "in_r"), (in_i, "in_i"), (out_r, "out_r"), (out_i, "out_i")):
+        _require_cuda(t, n)
+    check(
+        LIB.smc_cvnn_forward(
+            byref(net), params.data_ptr(), in_r.data_ptr(), in_i.data_ptr(), in_r.shape[0], out_r.data_ptr(),
+            out_i.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream(),
+        )
+    )
+
+
+def cvnn_loss_backward(net: CvnnNet, params: torch.Tensor, in_r: torch.Tensor, in_i: torch.Tensor, targets: torch.Tensor,
+                       grads: torch.Tensor, loss: torch.Tensor, workspace: torch.Tensor) -> None:
+    for t, n in ((params, "params"), (in_r, "in_r"), (in_i, "in_i"), (targets, "targets"), (grads, "grads"), (loss, "loss")):
+        _require_cuda(t, n)
+    check(
+        LIB.smc_cvnn_loss_backward(
+            byref(net), params.data_ptr(), in_r.data_ptr(), in_i.data_ptr(), targets.data_ptr(), in_r.shape[0],
+            grads.data_ptr(), loss.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream(),
+        )
+    )
+
+
+def adam_step(params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, step: torch.Tensor,
+              hyper: AdamArgs) -> None:
+    for t, n in ((params, "params"), (grads, "grads"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq"), (step, "step")):
+        _require_cuda(t, n)
+    check(
+        LIB.smc_adam_step(
+            params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), params.numel(),
+            dtype_code(params.dtype), step.data_ptr(), byref(hyper), _stream(),
+        )
+    )
+
+
+def cvnn_train_step(net: CvnnNet, params: torch.Tensor, grads: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                    step: torch.Tensor, hyper: AdamArgs, in_r: torch.Tensor, in_i: torch.Tensor, targets: torch.Tensor,
+                    loss: torch.Tensor, workspace: torch.Tensor) -> None:
+    for t, n in ((params, "params"), (in_r, "in_r"), (in_i, "in_i"), (targets, "targets"), (loss, "loss")):
+        _require_cuda(t, n)
+    check(
+        LIB.smc_cvnn_train_step(
+            byref(net), params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(), step.data_ptr(),
+            byref(hyper), in_r.data_ptr(), in_i.data_ptr(), targets.data_ptr(), in_r.shape[0], loss.data_ptr(),
+            workspace.data_ptr(), workspace.numel(), _stream(),
+        )
+    )

@@ -1,29 +1,53 @@
-"""Minimal complex-valued network — the downstream CONSUMER of the hot path's targets.
+"""Complex-valued network blocks consuming the hot path's ``[C, N]`` targets, and their fused step.
 
-Out of the hot-path scope (the CVNN "stays PyTorch"); this is just enough of the
-reference's ``spectralmc.cvnn`` surface (``ComplexLinear`` = four real matmuls, cvnn.py:65-146;
-``modReLU`` cvnn.py:168-210; ``ComplexSequential`` cvnn.py:439-470) to run a training step on the
-``[C, N]`` complex targets, with models mapping ``(real, imag) -> (real, imag)``.
+Two things live here:
+
+* the layer classes of the reference's ``spectralmc.cvnn`` that its pricer networks are made of —
+  ``ComplexLinear`` (cvnn.py:65-146: four real matmuls, Xavier-uniform weights, zero biases),
+  ``zReLU`` (:149-162), ``modReLU`` (:168-210, epsilon 1e-9 under the root) and
+  ``ComplexSequential`` (:439-452) — same constructor arguments, parameter names and forward
+  semantics, models mapping ``(real, imag) -> (real, imag)``.  Their ``forward`` is plain torch:
+  it is the generic route for networks the fused step does not cover (the batch norms and the
+  residual wrapper of the reference, cvnn.py:213-430,454-493, are not rebuilt).
+* ``FusedCVNN``: the same network driven through the C ABI (``smc_cvnn_forward``,
+  ``smc_cvnn_train_step``): one complex GEMM per ``ComplexLinear`` with bias and activation in
+  the epilogue, hand-derived backward, MSE loss and Adam (``GbmCVNNPricer._torch_step``,
+  gbm_trainer.py:819-835) as a fixed launch sequence with no host round trip, so a whole
+  training step replays as ONE CUDA graph.
 """
 
 from __future__ import annotations
 
-import math
+from functools import reduce
 
 import torch
 from torch import nn
 
+from spectralmc_b200 import _cabi
+
 
 class ComplexLinear(nn.Module):
+    """``W z + b`` with ``W = A + iB`` held as two real matrices (reference cvnn.py:65-146)."""
+
     def __init__(self, in_features: int, out_features: int, bias: bool = True) -> None:
         super().__init__()
+        self.in_features, self.out_features = in_features, out_features
         self.real_weight = nn.Parameter(torch.empty(out_features, in_features))
         self.imag_weight = nn.Parameter(torch.empty(out_features, in_features))
-        self.real_bias = nn.Parameter(torch.zeros(out_features)) if bias else None
-        self.imag_bias = nn.Parameter(torch.zeros(out_features)) if bias else None
-        bound = 1.0 / math.sqrt(in_features)
-        nn.init.uniform_(self.real_weight, -bound, bound)
-        nn.init.uniform_(self.imag_weight, -bound, bound)
+        if bias:
+            self.real_bias = nn.Parameter(torch.empty(out_features))
+            self.imag_bias = nn.Parameter(torch.empty(out_features))
+        else:
+            self.real_bias = None
+            self.imag_bias = None
+        self.reset_parameters()
+
+    def reset_parameters(self) -> None:
+        nn.init.xavier_uniform_(self.real_weight)
+        nn.init.xavier_uniform_(self.imag_weight)
+        if self.real_bias is not None:
+            nn.init.zeros_(self.real_bias)
+            nn.init.zeros_(self.imag_bias)
 
     def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         out_r = real @ self.real_weight.T - imag @ self.imag_weight.T
@@ -33,35 +57,195 @@ class ComplexLinear(nn.Module):
         return out_r, out_i
 
 
+class zReLU(nn.Module):
+    """Pass ``z`` where ``Re z >= 0`` and ``Im z >= 0``, else 0 (reference cvnn.py:149-162)."""
+
+    def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        mask = (real >= 0) & (imag >= 0)
+        return real * mask, imag * mask
+
+
 class modReLU(nn.Module):
-    """z -> ReLU(|z| + b) * z / |z|."""
+    """``z -> relu(|z| + b) * z / |z|`` with ``|z| = sqrt(x^2 + y^2 + 1e-9)`` (reference cvnn.py:168-210)."""
 
     def __init__(self, num_features: int) -> None:
         super().__init__()
         self.bias = nn.Parameter(torch.zeros(num_features))
 
     def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        mod = torch.sqrt(real * real + imag * imag + 1e-12)
-        scale = torch.relu(mod + self.bias) / mod
-        return real * scale, imag * scale
+        mod = torch.sqrt(real * real + imag * imag + 1e-9)
+        scale = torch.relu(mod + self.bias.unsqueeze(0)) / mod
+        return scale * real, scale * imag
 
 
 class ComplexSequential(nn.Module):
+    """Left fold of complex blocks (reference cvnn.py:439-452)."""
+
     def __init__(self, *layers: nn.Module) -> None:
         super().__init__()
         self.layers = nn.ModuleList(layers)
 
     def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
-        for layer in self.layers:
-            real, imag = layer(real, imag)
-        return real, imag
+        return reduce(lambda state, layer: layer(*state), self.layers, (real, imag))
 
 
 def make_cvnn(n_inputs: int, n_outputs: int, *, hidden_width: int = 32, seed: int = 0,
               dtype: torch.dtype = torch.float32, device: torch.device | str = "cuda") -> ComplexSequential:
     """6 -> hidden (modReLU) -> N, the shape of the reference's test network
-    (tests/helpers/factories.py:69-105); weights seeded inside a forked RNG as ``build_model`` does."""
+    (tests/helpers/factories.py:69-105), nested as the factory nests it (cvnn_factory.py:185-190);
+    weights seeded inside a forked RNG as ``build_model`` does (cvnn_factory.py:343-368)."""
     with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
-        net = ComplexSequential(ComplexLinear(n_inputs, hidden_width), modReLU(hidden_width), ComplexLinear(hidden_width, n_outputs))
+        net = ComplexSequential(ComplexSequential(ComplexLinear(n_inputs, hidden_width), modReLU(hidden_width)),
+                                ComplexLinear(hidden_width, n_outputs))
     return net.to(device=device, dtype=dtype)
+
+
+# ----------------------------------------------------------------------------- fused step
+def describe(module: nn.Module) -> list[tuple] | None:
+    """Flatten ``module`` into the C ABI's layer list, or ``None`` if it holds an unsupported block."""
+    if isinstance(module, ComplexSequential):
+        out: list[tuple] = []
+        for child in module.layers:
+            sub = describe(child)
+            if sub is None:
+                return None
+            out += sub
+        return out
+    if isinstance(module, ComplexLinear):
+        return [("linear", module.in_features, module.out_features, module.real_bias is not None)]
+    if isinstance(module, modReLU):
+        return [("modrelu", int(module.bias.numel()))]
+    if isinstance(module, zReLU):
+        return [("zrelu",)]
+    return None
+
+
+class FusedCVNN:
+    """A supported network + Adam state in flat device buffers, stepped through the C ABI.
+
+    Construction re-points every parameter of ``net`` at a view of one flat buffer (values
+    unchanged) and every ``.grad`` at a view of the flat gradient buffer, so the module keeps
+    working as a torch module (``state_dict``, torch ``forward``, gradient inspection); moving the
+    module afterwards (``.to()``) detaches it from the buffers and is not supported.
+    """
+
+    def __init__(self, net: nn.Module, *, lr: float = 1e-2, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
+        layers = describe(net)
+        if not layers:
+            raise ValueError("network is not a ComplexSequential of ComplexLinear / modReLU / zReLU")
+        params = list(net.parameters())
+        if not params:
+            raise ValueError("network has no parameters")
+        self.dtype, self.device = params[0].dtype, params[0].device
+        if self.device.type != "cuda":
+            raise ValueError("FusedCVNN needs the network on a CUDA device (spectralmc_b200 has no CPU path)")
+        if layers[0][0] == "zrelu":
+            raise ValueError("cannot infer the input width of a network that starts with zReLU")
+        self.n_inputs = layers[0][1]
+        self.net, self.layers = net, layers
+        self.desc, n = _cabi.make_cvnn_net(layers, self.n_inputs, self.dtype)
+        if n != sum(p.numel() for p in params):
+            raise AssertionError("descriptor / parameter count mismatch")
+        self.n_outputs = _cabi.cvnn_output_width(self.desc)
+        self.params = torch.empty(n, dtype=self.dtype, device=self.device)
+        self.grads = torch.zeros_like(self.params)
+        self.exp_avg = torch.zeros_like(self.params)
+        self.exp_avg_sq = torch.zeros_like(self.params)
+        self.step = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.hyper = _cabi.AdamArgs(lr, betas[0], betas[1], eps)
+        self._slices: list[tuple[int, int]] = []
+        offset = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                self.params[offset : offset + k].copy_(p.detach().reshape(-1))
+                p.data = self.params[offset : offset + k].view(p.shape)
+                p.grad = self.grads[offset : offset + k].view(p.shape)
+                self._slices.append((offset, k))
+                offset += k
+        self._workspaces: dict[tuple[int, bool], torch.Tensor] = {}
+
+    def _workspace(self, rows: int, training: bool) -> torch.Tensor:
+        key = (rows, training)
+        ws = self._workspaces.get(key)
+        if ws is None:
+            ws = torch.empty(_cabi.cvnn_workspace_bytes(self.desc, rows, training), dtype=torch.uint8, device=self.device)
+            self._workspaces[key] = ws
+        return ws
+
+    def _check_inputs(self, real: torch.Tensor, imag: torch.Tensor) -> int:
+        if real.shape != imag.shape or real.dim() != 2 or real.shape[1] != self.n_inputs:
+            raise ValueError(f"inputs must be two [rows, {self.n_inputs}] tensors")
+        if real.dtype != self.dtype or imag.dtype != self.dtype:
+            raise TypeError(f"inputs must be {self.dtype}")
+        return real.shape[0]
+
+    def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        rows = self._check_inputs(real, imag)
+        out_r = torch.empty((rows, self.n_outputs), dtype=self.dtype, device=self.device)
+        out_i = torch.empty_like(out_r)
+        if rows:
+            _cabi.cvnn_forward(self.desc, self.params, real.contiguous(), imag.contiguous(), out_r, out_i, self._workspace(rows, False))
+        return out_r, out_i
+
+    __call__ = forward
+
+    def _check_targets(self, rows: int, targets: torch.Tensor) -> torch.Tensor:
+        if targets.shape != (rows, self.n_outputs) or targets.dtype != _cabi.complex_dtype(self.dtype):
+            raise ValueError(f"targets must be [{rows}, {self.n_outputs}] {_cabi.complex_dtype(self.dtype)}")
+        return torch.view_as_real(targets.contiguous())
+
+    def loss_backward(self, real: torch.Tensor, imag: torch.Tensor, targets: torch.Tensor, loss: torch.Tensor | None = None) -> torch.Tensor:
+        """Forward, ``mse(real) + mse(imag)`` and every gradient (``p.grad`` views); returns the device loss."""
+        rows = self._check_inputs(real, imag)
+        loss = torch.empty(1, dtype=torch.float64, device=self.device) if loss is None else loss
+        _cabi.cvnn_loss_backward(self.desc, self.params, real.contiguous(), imag.contiguous(), self._check_targets(rows, targets),
+                                 self.grads, loss, self._workspace(rows, True))
+        return loss
+
+    def train_step(self, real: torch.Tensor, imag: torch.Tensor, targets: torch.Tensor, loss: torch.Tensor | None = None) -> torch.Tensor:
+        """One ``_torch_step`` (gbm_trainer.py:819-835): loss, backward, Adam.  No host synchronisation."""
+        rows = self._check_inputs(real, imag)
+        loss = torch.empty(1, dtype=torch.float64, device=self.device) if loss is None else loss
+        _cabi.cvnn_train_step(self.desc, self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step, self.hyper,
+                              real.contiguous(), imag.contiguous(), self._check_targets(rows, targets), loss,
+                              self._workspace(rows, True))
+        return loss
+
+    def warm_up(self, rows: int) -> None:
+        """Launch every kernel of a step once WITHOUT touching parameters or optimiser state, so
+        module loading cannot fall inside a graph capture."""
+        real = torch.zeros((rows, self.n_inputs), dtype=self.dtype, device=self.device)
+        targets = torch.zeros((rows, self.n_outputs), dtype=_cabi.complex_dtype(self.dtype), device=self.device)
+        scratch = [torch.zeros(1, dtype=self.dtype, device=self.device) for _ in range(4)]
+        grads = torch.empty_like(self.grads)
+        loss = torch.empty(1, dtype=torch.float64, device=self.device)
+        _cabi.cvnn_loss_backward(self.desc, self.params, real, real, torch.view_as_real(targets), grads, loss, self._workspace(rows, True))
+        _cabi.adam_step(scratch[0], scratch[1], scratch[2], scratch[3], torch.zeros(1, dtype=torch.int64, device=self.device), self.hyper)
+
+    # ---- optimiser state in torch.optim.Adam's state_dict layout (snapshot interchange) -----
+    def optimizer_state_dict(self) -> dict:
+        step = float(self.step.item())
+        state = {}
+        if step > 0:
+            for i, (p, (o, k)) in enumerate(zip(self.net.parameters(), self._slices)):
+                state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o : o + k].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o : o + k].view(p.shape).clone()}
+        group = {"lr": self.hyper.lr, "betas": (self.hyper.beta1, self.hyper.beta2), "eps": self.hyper.eps, "weight_decay": 0,
+                 "amsgrad": False, "params": list(range(len(self._slices)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd: dict) -> None:
+        group = sd["param_groups"][0]
+        self.hyper = _cabi.AdamArgs(group["lr"], group["betas"][0], group["betas"][1], group["eps"])
+        steps = {float(s["step"]) for s in sd["state"].values()}
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ")
+        self.step.fill_(int(steps.pop()) if steps else 0)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (o, k) in enumerate(self._slices):
+            if i in sd["state"]:
+                self.exp_avg[o : o + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o : o + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
