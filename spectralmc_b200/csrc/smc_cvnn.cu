@@ -30,9 +30,13 @@ namespace {
 
 constexpr int BLK = 256;
 constexpr int TI = 32, TJ = 32, TL = 16;     // cgemm tile
-constexpr int64_t SPLIT_ROWS = 256;           // rows of the batch per weight-gradient split
-constexpr int64_t MAX_SPLITS = 128;
-constexpr int64_t COLSUM_SLAB = 1024;         // rows per column-sum slab
+// The step is latency-bound at the reference's sizes (a thousand rows, widths 6..256), so the
+// reductions over the batch are cut into many short, independent pieces: 64-row weight-gradient
+// splits and 128-row column-sum slabs, each followed by a fixed-order second pass.
+constexpr int64_t SPLIT_ROWS = 64;            // rows of the batch per weight-gradient split
+constexpr int64_t MAX_SPLITS = 256;
+constexpr int64_t COLSUM_SLAB = 128;          // rows per column-sum slab
+constexpr int COLSUM_PLANES = 3;
 constexpr int64_t LOSS_CHUNK = 4096;          // elements per CTA of the loss kernel
 constexpr double MODRELU_EPS = 1e-9;          // cvnn.py:205
 
@@ -158,24 +162,34 @@ __global__ void __launch_bounds__(BLK)
   dst_i[e] = si;
 }
 
-// column sums of a [rows, cols] plane: slab s of COLSUM_SLAB rows -> out[s * cols + j]
+// column sums of up to three [rows, cols] planes in one launch: plane z, slab y of COLSUM_SLAB rows
+// (slab_rows rows) -> dst[z][y * cols + j]
+template <typename Real>
+struct ColsumJob {
+  const Real* src[COLSUM_PLANES];
+  Real* dst[COLSUM_PLANES];
+};
+
 template <typename Real>
 __global__ void __launch_bounds__(BLK)
-    colsum_kernel(const Real* __restrict__ src, int64_t rows, int64_t cols, Real* __restrict__ out) {
+    colsum_kernel(const ColsumJob<Real> job, int64_t rows, int64_t cols, int64_t slab_rows) {
   __shared__ Real sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const Real* __restrict__ src = job.src[blockIdx.z];
   const int64_t j = static_cast<int64_t>(blockIdx.x) * 32 + tx;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * COLSUM_SLAB, r1 = min(r0 + COLSUM_SLAB, rows);
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * slab_rows, r1 = min(r0 + slab_rows, rows);
   Real s = 0;
-  if (j < cols)
+  if (j < cols) {
+#pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += 8) s += src[r * cols + j];
+  }
   sm[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && j < cols) {
     Real tot = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) tot += sm[k][tx];
-    out[static_cast<int64_t>(blockIdx.y) * cols + j] = tot;
+    job.dst[blockIdx.z][static_cast<int64_t>(blockIdx.y) * cols + j] = tot;
   }
 }
 
@@ -388,7 +402,7 @@ int build_plan(const char* fn, const smc_cvnn_net* net, int64_t rows, bool train
     for (const Node& nd : plan->nodes)
       if (nd.linear) max_w_elems = std::max(max_w_elems, nd.in_w * nd.out_w);
     plan->wpart = take(static_cast<size_t>(splits) * 2 * max_w_elems * rs);
-    plan->colpart = take(static_cast<size_t>((rows + COLSUM_SLAB - 1) / COLSUM_SLAB) * plan->max_w * rs);
+    plan->colpart = take(static_cast<size_t>(COLSUM_PLANES) * ((rows + COLSUM_SLAB - 1) / COLSUM_SLAB) * plan->max_w * rs);
     plan->losspart = take(static_cast<size_t>((rows * plan->out_w + LOSS_CHUNK - 1) / LOSS_CHUNK) * 2 * sizeof(double));
   }
   plan->total = used + 256;
@@ -408,20 +422,28 @@ int launch_gemm(const GemmParams<Real>& p, bool conj_b, int64_t splits, cudaStre
   return SMC_OK;
 }
 
-// out[j] = sum over rows of src[:, j]   (one or two fixed-order passes)
+// dst[z][j] = sum over rows of src[z][:, j] for n <= 3 planes (one or two fixed-order passes)
 template <typename Real>
-int column_sum(const Real* src, int64_t rows, int64_t cols, Real* out, Real* scratch, cudaStream_t st) {
+int column_sums(const Real* const* src, Real* const* dst, int n, int64_t rows, int64_t cols, Real* scratch,
+                cudaStream_t st) {
+  if (n == 0) return SMC_OK;
   const int64_t slabs = (rows + COLSUM_SLAB - 1) / COLSUM_SLAB;
   const unsigned gx = static_cast<unsigned>((cols + 31) / 32);
-  if (slabs == 1) {
-    colsum_kernel<Real><<<dim3(gx, 1), BLK, 0, st>>>(src, rows, cols, out);
-    SMC_LAUNCH_OK("colsum_kernel");
-    return SMC_OK;
+  SMC_REQUIRE(slabs <= 65535, "cvnn: too many rows for the column sum (%lld)", (long long)rows);
+  ColsumJob<Real> job{};
+  for (int z = 0; z < n; ++z) {
+    job.src[z] = src[z];
+    job.dst[z] = slabs == 1 ? dst[z] : scratch + static_cast<int64_t>(z) * slabs * cols;
   }
-  SMC_REQUIRE(slabs <= COLSUM_SLAB, "cvnn: more than %lld rows are not supported", (long long)(COLSUM_SLAB * COLSUM_SLAB));
-  colsum_kernel<Real><<<dim3(gx, static_cast<unsigned>(slabs)), BLK, 0, st>>>(src, rows, cols, scratch);
+  colsum_kernel<Real><<<dim3(gx, static_cast<unsigned>(slabs), n), BLK, 0, st>>>(job, rows, cols, COLSUM_SLAB);
   SMC_LAUNCH_OK("colsum_kernel");
-  colsum_kernel<Real><<<dim3(gx, 1), BLK, 0, st>>>(scratch, slabs, cols, out);  // slab partials, fixed order
+  if (slabs == 1) return SMC_OK;
+  for (int z = 0; z < n; ++z) {
+    job.src[z] = job.dst[z];
+    job.dst[z] = dst[z];
+  }
+  // the slab partials of a plane form one [slabs, cols] matrix, summed as a single slab
+  colsum_kernel<Real><<<dim3(gx, 1, n), BLK, 0, st>>>(job, slabs, cols, slabs);
   SMC_LAUNCH_OK("colsum_kernel");
   return SMC_OK;
 }
@@ -495,14 +517,19 @@ int run_loss_backward(const Plan& plan, const Real* params, const Real* in_r, co
       act_backward_kernel<Real><<<static_cast<unsigned>((n_out + BLK - 1) / BLK), BLK, 0, st>>>(
           gr, gi, zr, zi, n_out, nd.out_w, nd.act, nd.act == ACT_MODRELU ? params + nd.act_off : nullptr, bterm);
       SMC_LAUNCH_OK("act_backward_kernel");
-      if (nd.act == ACT_MODRELU)
-        if (int rc = column_sum<Real>(bterm, rows, nd.out_w, grads + nd.act_off, colpart, st)) return rc;
+    }
+    {  // bias gradients: column sums of gr, gi (ComplexLinear bias) and of the modReLU bias term, one launch
+      const Real* src[COLSUM_PLANES];
+      Real* dst[COLSUM_PLANES];
+      int n = 0;
+      if (nd.linear && nd.has_bias) {
+        src[n] = gr; dst[n++] = grads + nd.b_off;
+        src[n] = gi; dst[n++] = grads + nd.b_off + nd.out_w;
+      }
+      if (nd.act == ACT_MODRELU) { src[n] = bterm; dst[n++] = grads + nd.act_off; }
+      if (int rc = column_sums<Real>(src, dst, n, rows, nd.out_w, colpart, st)) return rc;
     }
     if (!nd.linear) continue;  // (gr, gi) is now the gradient wrt this node's input, same width
-    if (nd.has_bias) {
-      if (int rc = column_sum<Real>(gr, rows, nd.out_w, grads + nd.b_off, colpart, st)) return rc;
-      if (int rc = column_sum<Real>(gi, rows, nd.out_w, grads + nd.b_off + nd.out_w, colpart, st)) return rc;
-    }
     {  // dW[o, k] = sum_m G[m, o] conj(X[m, k]):  dA = gr^T xr + gi^T xi ; dB = gi^T xr - gr^T xi
       const int64_t splits = std::min<int64_t>(MAX_SPLITS, (rows + SPLIT_ROWS - 1) / SPLIT_ROWS);
       const int64_t welems = nd.in_w * nd.out_w;
