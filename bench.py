@@ -45,7 +45,7 @@ WORKLOADS = {
     "c4": dict(contracts=512, T=365, N=256, B=4096, dtype="float64"),
 }
 # SASS-counted work per fp32 path-step of the fused log-Euler kernel (profiles/ has the listing):
-ISSUE_SLOTS_PER_STEP = 15.08  # warp-instructions issued per path-step per lane (181 per two 6-normal blocks, SASS)
+ISSUE_SLOTS_PER_STEP = 163.0 / 12.0  # warp-instructions issued per path-step per lane (163 per two 6-normal blocks, SASS: profiles/r1_fused_f32_sass_inner_loop.txt)
 XU_OPS_PER_STEP = 2.0  # (LG2 + SQRT + SIN + COS) per Box–Muller pair / 2 normals; log-sum variant
 
 

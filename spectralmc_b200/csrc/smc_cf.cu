@@ -185,8 +185,22 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
 #define SMC_F32_UNROLL 2  // codegen knob, see profiles/r1_codegen_variant_matrix.txt
 #endif
   constexpr int kUnroll = SMC_F32_UNROLL;
+#ifndef SMC_F32X2
+#define SMC_F32X2 1  // packed FADD2/FMUL2/FFMA2 Box-Muller over two row groups at a time (log-Euler sum only): 163 vs 181 issue slots per 12 normals
+#endif
+  uint32_t q = 0;
+  if (SMC_F32X2 && SCHEME == SMC_LOG_EULER && !REFINE) {
+    float2 acc2 = make_float2(0.0f, 0.0f);
+#ifndef SMC_F32X2_UNROLL
+#define SMC_F32X2_UNROLL 1
+#endif
+    constexpr int kUnrollX2 = SMC_F32X2_UNROLL;
+#pragma unroll kUnrollX2
+    for (; q + 1 < nq; q += 2) acc2 = normals12_sum_f32x2(col, q, k_lo, k_hi, keys, acc2, min_word);
+    acc = acc2.x + acc2.y;
+  }
 #pragma unroll kUnroll
-  for (uint32_t q = 0; q < nq; ++q) {
+  for (; q < nq; ++q) {
     float z[6];
     normals6_f32_impl<REFINE>(col, q, k_lo, k_hi, keys, z, min_word);
 #ifndef SMC_SUM_TREE
@@ -287,7 +301,7 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
 #endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 4  // with SMC_F32_UNROLL=2, SMC_BM_ORDER=2: measured best (profiles/r1_codegen_variant_matrix.txt)
+#define SMC_F32_FUSED_MIN_CTAS 5  // with SMC_F32X2=1: measured best (1.322 ms vs 1.385 at 4, 1.341 at 6; profiles/r1_codegen_variant_matrix.txt)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM

@@ -181,6 +181,68 @@ __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint
 #endif
 }
 
+// ---- packed FP32 (sm_100 FADD2 / FMUL2 / FFMA2: two float lanes per issue slot) -------------
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a.x, a.y)), "l"(pack_f32x2(b.x, b.y)));
+  return unpack_f32x2(d);
+}
+__device__ __forceinline__ float2 mul_f32x2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("mul.rn.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack_f32x2(a.x, a.y)), "l"(pack_f32x2(b.x, b.y)));
+  return unpack_f32x2(d);
+}
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.ftz.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(pack_f32x2(a.x, a.y)), "l"(pack_f32x2(b.x, b.y)), "l"(pack_f32x2(c.x, c.y)));
+  return unpack_f32x2(d);
+}
+
+// Two Box–Muller pairs at once, accumulated: acc += (z_even, z_odd) of pair A in lane x and of
+// pair B in lane y.  Same values per lane as box_muller_f32 (identical operations, packed).
+__device__ __forceinline__ float2 box_muller_sum_f32x2(float2 radius_unit, float2 angle_unit, float2 acc) {
+  const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffff8p-1f, -0x1.fffff8p-1f));
+  const float2 theta = fma_f32x2(angle_unit, make_float2(6.28318530717958648f, 6.28318530717958648f),
+                                 make_float2(-9.424776462741265f, -9.424776462741265f));
+  const float2 m = mul_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)),
+                             make_float2(-1.38629436111989062f, -1.38629436111989062f));
+  const float2 r = make_float2(mufu_sqrt(m.x), mufu_sqrt(m.y));
+  acc = fma_f32x2(r, make_float2(mufu_cos(theta.x), mufu_cos(theta.y)), acc);
+  return fma_f32x2(r, make_float2(mufu_sin(theta.x), mufu_sin(theta.y)), acc);
+}
+
+// Sum of the 12 normals of row groups q and q + 1 (coarse radius uniforms, like REFINE = false),
+// added to acc.x + acc.y.  Three packed Box–Muller evaluations over the six pairs.
+__device__ __forceinline__ float2 normals12_sum_f32x2(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                                      const PhiloxKeys& key, float2 acc, uint32_t& min_word) {
+  uint32_t x[4], y[4];
+  philox4x32_10(col, q, k_lo, k_hi, key, x);
+  philox4x32_10(col, q + 1u, k_lo, k_hi, key, y);
+  min_word = min(min(min_word, x[0]), min(x[1], x[2]));
+  min_word = min(min(min_word, y[0]), min(y[1], y[2]));
+  const float ax0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
+  const float ax1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
+  const float ax2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
+  const float ay0 = unit_float_21(__funnelshift_l(y[3], y[0], 12));
+  const float ay1 = unit_float_21(__funnelshift_l(y[3] << 10, y[1], 12));
+  const float ay2 = unit_float_21(__funnelshift_l(y[3] << 20, y[2], 12));
+  acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[0] >> 9), unit_float_21(y[0] >> 9)), make_float2(ax0, ay0), acc);
+  acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[1] >> 9), unit_float_21(y[1] >> 9)), make_float2(ax1, ay1), acc);
+  return box_muller_sum_f32x2(make_float2(unit_float_21(x[2] >> 9), unit_float_21(y[2] >> 9)), make_float2(ax2, ay2), acc);
+}
+
 __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                              const PhiloxKeys& key, float (&z)[6]) {
   uint32_t unused = 0;

@@ -4,7 +4,7 @@
 usage: python tools/sass_loop.py <mangled-name-prefix> [--dump]
 """
 import collections, re, subprocess, sys, os
-lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spectralmc_b200", "lib", "libspectralmc_b200.so")
+lib = os.environ.get("SPECTRALMC_B200_LIB") or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "spectralmc_b200", "lib", "libspectralmc_b200.so")
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 for part in re.split(r"\n\s*Function : ", txt)[1:]:
     if not part.startswith(sys.argv[1]):
