@@ -130,3 +130,53 @@ class SamplerValidationFailed:
 
 
 SamplerError = Union[DimensionMismatch, InvalidBounds, BoundSpecInvalid, NegativeSamples, SamplerValidationFailed]
+
+
+# ---- trainer (errors/trainer.py; gbm_trainer.py:525-555) --------------------------------------
+@dataclass(frozen=True)
+class SamplerInitFailed:
+    error: object
+    kind: Literal["SamplerInitFailed"] = "SamplerInitFailed"
+
+
+@dataclass(frozen=True)
+class InvalidTrainerConfig:
+    message: str
+    kind: Literal["InvalidTrainerConfig"] = "InvalidTrainerConfig"
+
+
+@dataclass(frozen=True)
+class InvalidTrainingConfig:
+    num_batches: int
+    batch_size: int
+    learning_rate: float
+    message: str
+    kind: Literal["InvalidTrainingConfig"] = "InvalidTrainingConfig"
+
+
+@dataclass(frozen=True)
+class OptimizerStateSerializationFailed:
+    message: str
+    kind: Literal["OptimizerStateSerializationFailed"] = "OptimizerStateSerializationFailed"
+
+
+@dataclass(frozen=True)
+class PredictionFailed:
+    message: str
+    kind: Literal["PredictionFailed"] = "PredictionFailed"
+
+
+@dataclass(frozen=True)
+class DeviceDTypeError:
+    """The CVNN's parameters do not share one device / full-precision dtype, or the dtype differs
+    from the simulation's (the reference asserts the latter, gbm_trainer.py:685-687)."""
+
+    message: str
+    kind: Literal["DeviceDTypeError"] = "DeviceDTypeError"
+
+
+@dataclass(frozen=True)
+class DeviceNotCUDA:
+    device: str
+    message: str
+    kind: Literal["DeviceNotCUDA"] = "DeviceNotCUDA"

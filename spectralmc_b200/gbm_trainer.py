@@ -6,6 +6,14 @@ Covers what SURVEY.md §8a puts on the hot path from /root/reference/src/spectra
 ``_torch_step`` :819-835), ``_split_inputs`` :1775-1783, ``predict_price`` :1709-1735 and the
 ``snapshot`` bookkeeping (``sobol_skip``, ``global_step``, engine ``skip``) :756-800.  The
 reference's commit plans, S3 store, TensorBoard logging and effect descriptions are out of scope.
+The public shape follows the reference: ``build_training_config`` :261-298, ``GbmCVNNPricerConfig``
+:301-313, ``StepMetrics`` / ``TrainingResult`` :336-361, ``GbmCVNNPricer.create(cfg) -> Result``
+:600-663, ``train(config, logger=...) -> Result[TrainingResult, ...]`` :1456-1683,
+``snapshot() -> Result[GbmCVNNPricerConfig, ...]`` :756-800 and
+``predict_price(inputs) -> Result[list[HostPricingResults], ...]`` :1709-1769, so the reference's
+tests/test_gbm_trainer.py reads the same against this module.  Deviation: ``optimizer_state`` is
+``torch.optim.Adam.state_dict()`` with CPU tensors (the reference wraps the same dictionary in its
+``AdamOptimizerState`` serialisation model, out of scope here).
 
 The per-contract Python loop with >= 5 host synchronisations per contract becomes
 ONE C-ABI call per training step; targets are produced directly as a torch tensor, so the
@@ -22,18 +30,30 @@ takes the generic torch route below (``fused_step=False`` forces it).
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Sequence
+import math
+import time
+import warnings
+from dataclasses import dataclass
+from typing import Callable, Sequence
 
 import numpy as np
 import torch
+from pydantic import BaseModel, ConfigDict
 from torch import nn, optim
 
 from spectralmc_b200.cvnn import FusedCVNN, describe
 from spectralmc_b200.distributed import sharded_cf_targets
+from spectralmc_b200.errors import (
+    DeviceDTypeError,
+    DeviceNotCUDA,
+    InvalidTrainingConfig,
+    PredictionFailed,
+    SamplerInitFailed,
+)
 from spectralmc_b200.gbm import BlackScholes, BlackScholesConfig
 from spectralmc_b200.result import Failure, Result, Success
 from spectralmc_b200.sobol_sampler import DomainBounds, SobolConfig, SobolSampler
+from spectralmc_b200.validation import validate_model
 
 
 def _split_inputs(rows: np.ndarray | Sequence[BlackScholes.Inputs], *, dtype: torch.dtype, device: torch.device) -> tuple[torch.Tensor, torch.Tensor]:
@@ -45,24 +65,115 @@ def _split_inputs(rows: np.ndarray | Sequence[BlackScholes.Inputs], *, dtype: to
     return real, torch.zeros_like(real)
 
 
-@dataclass
+@dataclass(frozen=True)
 class TrainingConfig:
+    """Training hyper-parameters (reference :252-258); validate with ``build_training_config``."""
+
     num_batches: int
     batch_size: int
     learning_rate: float = 1e-2
 
 
-@dataclass
-class PricerSnapshot:
+def build_training_config(*, num_batches: int, batch_size: int, learning_rate: float) -> Result[TrainingConfig, InvalidTrainingConfig]:
+    """Reference :261-298: positive counts, learning rate in (0, 1)."""
+
+    def bad(message: str) -> Failure[InvalidTrainingConfig]:
+        return Failure(InvalidTrainingConfig(num_batches=num_batches, batch_size=batch_size, learning_rate=learning_rate, message=message))
+
+    if num_batches <= 0:
+        return bad("num_batches must be > 0")
+    if batch_size <= 0:
+        return bad("batch_size must be > 0")
+    if not (0.0 < learning_rate < 1.0):
+        return bad("learning_rate must be in (0, 1)")
+    return Success(TrainingConfig(num_batches=num_batches, batch_size=batch_size, learning_rate=learning_rate))
+
+
+class GbmCVNNPricerConfig(BaseModel):
+    """Frozen snapshot of a trainer (reference :301-313)."""
+
     cfg: BlackScholesConfig
-    sobol_skip: int
-    global_step: int
-    cvnn_state: dict = field(default_factory=dict)
-    optimizer_state: dict | None = None
+    domain_bounds: DomainBounds
+    cvnn: nn.Module
+    optimizer_state: dict | None = None  # torch.optim.Adam.state_dict() layout, CPU tensors
+    global_step: int = 0
+    sobol_skip: int = 0
+    torch_cpu_rng_state: bytes | None = None
+    torch_cuda_rng_states: list[bytes] | None = None
+
+    model_config = ConfigDict(arbitrary_types_allowed=True, frozen=True, extra="forbid")
+
+
+def build_gbm_cvnn_pricer_config(**kwargs: object) -> Result[GbmCVNNPricerConfig, object]:
+    return validate_model(GbmCVNNPricerConfig, **kwargs)
+
+
+@dataclass(frozen=True)
+class StepMetrics:
+    """Scalars handed to the ``logger`` callback after every optimiser step (reference :336-346).
+    ``optimizer`` is the ``torch.optim.Adam`` of the torch route or the ``FusedCVNN`` of the C-ABI route."""
+
+    step: int
+    batch_time: float
+    loss: float
+    grad_norm: float
+    lr: float
+    optimizer: object
+    model: nn.Module
+
+
+StepLogger = Callable[[StepMetrics], None]
+
+
+@dataclass(frozen=True)
+class TrainingResult:
+    """Outcome of ``train`` (reference :349-361) plus the per-step losses, which this implementation
+    keeps on the device during the run and reads back once."""
+
+    updated_config: GbmCVNNPricerConfig
+    final_loss: float
+    total_batches: int
+    final_grad_norm: float
+    losses: tuple[float, ...] = ()
+
+
+def _module_device_dtype(module: nn.Module) -> Result[tuple[torch.device, torch.dtype], DeviceDTypeError]:
+    tensors = list(module.state_dict().values())
+    if not tensors:
+        return Failure(DeviceDTypeError(message="CVNN has no parameters"))
+    devices, dtypes = {t.device for t in tensors}, {t.dtype for t in tensors}
+    if len(devices) != 1 or len(dtypes) != 1:
+        return Failure(DeviceDTypeError(message=f"CVNN tensors span devices {sorted(map(str, devices))} / dtypes {sorted(map(str, dtypes))}"))
+    dtype = dtypes.pop()
+    if dtype not in (torch.float32, torch.float64):
+        return Failure(DeviceDTypeError(message=f"CVNN must use float32 or float64 parameters, got {dtype}"))
+    return Success((devices.pop(), dtype))
 
 
 class GbmCVNNPricer:
     """Trains a CVNN on CF targets produced by the fused Monte-Carlo path."""
+
+    @staticmethod
+    def create(cfg: GbmCVNNPricerConfig, *, process_group=None, fused_step: bool | None = None,
+               cuda_graph: bool = True) -> Result["GbmCVNNPricer", DeviceDTypeError | DeviceNotCUDA]:
+        """Validated construction (reference :600-663): the CVNN must live on one CUDA device in the
+        simulation's precision."""
+        got = _module_device_dtype(cfg.cvnn)
+        if isinstance(got, Failure):
+            return got
+        device, dtype = got.value
+        if device.type != "cuda":
+            return Failure(DeviceNotCUDA(device=str(device), message=f"Model on {device}, but CUDA required for training"))
+        if dtype != cfg.cfg.sim_params.dtype.to_torch():
+            return Failure(DeviceDTypeError(message=f"gbm sim dtype {cfg.cfg.sim_params.dtype} does not match cvnn dtype {dtype}"))
+        self = GbmCVNNPricer(cfg.cfg, cfg.domain_bounds, cfg.cvnn, sobol_skip=cfg.sobol_skip, global_step=cfg.global_step,
+                             process_group=process_group, fused_step=fused_step, cuda_graph=cuda_graph)
+        self._optimizer_state = cfg.optimizer_state
+        if cfg.torch_cpu_rng_state is not None:  # reference :714-721
+            torch.set_rng_state(torch.from_numpy(np.frombuffer(cfg.torch_cpu_rng_state, dtype=np.uint8).copy()))
+        if cfg.torch_cuda_rng_states is not None and len(cfg.torch_cuda_rng_states) == torch.cuda.device_count():
+            torch.cuda.set_rng_state_all([torch.from_numpy(np.frombuffer(b, dtype=np.uint8).copy()) for b in cfg.torch_cuda_rng_states])
+        return Success(self)
 
     def __init__(self, cfg: BlackScholesConfig, domain_bounds: DomainBounds, cvnn: nn.Module, *, sobol_skip: int = 0,
                  global_step: int = 0, process_group=None, fused_step: bool | None = None, cuda_graph: bool = True) -> None:
@@ -74,7 +185,7 @@ class GbmCVNNPricer:
         self._domain_bounds = domain_bounds
         self._sobol_skip, self._global_step = sobol_skip, global_step
         self._group = process_group
-        self._optimizer: optim.Optimizer | None = None
+        self._optimizer_state: dict | None = None  # Adam state between train() calls (reference :671, :1646)
         supported = describe(cvnn) is not None
         if fused_step and not supported:
             raise ValueError("fused_step=True needs a ComplexSequential of ComplexLinear / modReLU / zReLU")
@@ -101,14 +212,15 @@ class GbmCVNNPricer:
             return Success(sharded_cf_targets(self._engine, dev, group=self._group))
         return self._engine.cf_targets(dev)
 
-    def _torch_step(self, real_in, imag_in, targets, optimizer) -> tuple[torch.Tensor, float]:
-        """Forward / MSE on real and imaginary parts / backward / Adam (reference :819-835)."""
+    def _torch_step(self, real_in, imag_in, targets, optimizer) -> tuple[torch.Tensor, torch.Tensor]:
+        """Forward / MSE on real and imaginary parts / backward / Adam (reference :819-835); the
+        gradient norm stays a device scalar (the reference converts it to a float every step)."""
         pred_r, pred_i = self._cvnn(real_in, imag_in)
         loss = nn.functional.mse_loss(pred_r, torch.real(targets)) + nn.functional.mse_loss(pred_i, torch.imag(targets))
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
         optimizer.step()
-        grad_norm = float(torch.nn.utils.clip_grad_norm_(self._cvnn.parameters(), float("inf")))
+        grad_norm = torch.nn.utils.clip_grad_norm_(self._cvnn.parameters(), float("inf"))
         return loss, grad_norm
 
     def _fused_step(self, contracts: torch.Tensor, targets: torch.Tensor, loss_slot: torch.Tensor) -> None:
@@ -128,23 +240,41 @@ class GbmCVNNPricer:
         g.graph.replay()
         loss_slot.copy_(g.loss)
 
-    def train(self, config: TrainingConfig) -> Result[list[float], object]:
+    def _attach_optimizer(self, learning_rate: float) -> object:
+        """A fresh Adam per ``train`` call with the previous call's state re-attached (reference :1513-1529)."""
+        if self._use_fused:
+            if self._fused is None:
+                self._fused = FusedCVNN(self._cvnn, lr=learning_rate)
+            elif self._fused.hyper.lr != learning_rate:
+                self._fused.hyper.lr = learning_rate  # hyper-parameters are baked into captured launches
+                self._graphs.clear()
+            if self._optimizer_state is not None:
+                self._fused.load_optimizer_state_dict(dict(self._optimizer_state, param_groups=[
+                    dict(self._optimizer_state["param_groups"][0], lr=learning_rate)]))
+                self._optimizer_state = None  # now lives in the fused buffers until the next snapshot
+            return self._fused
+        adam = optim.Adam(self._cvnn.parameters(), lr=learning_rate)
+        if self._optimizer_state is not None:
+            adam.load_state_dict(self._optimizer_state)
+            for group in adam.param_groups:
+                group["lr"] = learning_rate
+        return adam
+
+    def train(self, config: TrainingConfig, *, logger: StepLogger | None = None) -> Result[TrainingResult, object]:
+        """``config.num_batches`` optimiser steps (reference :1456-1683).  Without a ``logger`` nothing
+        synchronises the host until the losses are read back at the end."""
         if isinstance(self._sampler_result, Failure):
-            return self._sampler_result
+            return Failure(SamplerInitFailed(error=self._sampler_result.error))
         sampler = self._sampler_result.value
-        if self._use_fused and self._fused is None:
-            self._fused = FusedCVNN(self._cvnn, lr=config.learning_rate)
-        elif self._use_fused and self._fused.hyper.lr != config.learning_rate:
-            self._fused.hyper.lr = config.learning_rate  # hyper-parameters are baked into captured launches
-            self._graphs.clear()
-        elif not self._use_fused and self._optimizer is None:
-            self._optimizer = optim.Adam(self._cvnn.parameters(), lr=config.learning_rate)
+        optimizer = self._attach_optimizer(config.learning_rate)
         self._cvnn.train()
         losses = torch.zeros(max(config.num_batches, 1), dtype=torch.float64, device=self._device)
+        grad_norm: torch.Tensor | None = None
         for i in range(config.num_batches):
+            t0 = time.perf_counter()
             drawn = sampler.sample_array(config.batch_size)
             if isinstance(drawn, Failure):
-                return drawn
+                return Failure(SamplerInitFailed(error=drawn.error))
             self._sobol_skip += config.batch_size
             contracts = self._upload(drawn.value)
             got = self.targets(contracts)
@@ -155,56 +285,76 @@ class GbmCVNNPricer:
                 self._fused_step(contracts, targets, losses[i : i + 1])
             else:
                 real_in = contracts.to(self._dtype)
-                loss, _ = self._torch_step(real_in, torch.zeros_like(real_in), targets, self._optimizer)
+                loss, grad_norm = self._torch_step(real_in, torch.zeros_like(real_in), targets, optimizer)
                 losses[i : i + 1].copy_(loss.detach())
             self._global_step += 1
-        return Success([float(x) for x in losses[: config.num_batches].cpu()])
+            if logger is not None:  # per-step host metrics, as the reference produces them (:1567-1583)
+                gn = self._fused.grads.norm() if self._use_fused else grad_norm
+                logger(StepMetrics(step=self._global_step, batch_time=time.perf_counter() - t0, loss=float(losses[i]),
+                                   grad_norm=float(gn), lr=config.learning_rate, optimizer=optimizer, model=self._cvnn))
+        if config.num_batches > 0:
+            grad_norm = self._fused.grads.norm() if self._use_fused else grad_norm
+        host = [float(x) for x in losses[: config.num_batches].cpu()]
+        if not self._use_fused:
+            self._optimizer_state = _to_cpu(optimizer.state_dict())
+        snap = self.snapshot()
+        if isinstance(snap, Failure):
+            return snap
+        return Success(TrainingResult(updated_config=snap.value, final_loss=host[-1] if host else 0.0, total_batches=config.num_batches,
+                                      final_grad_norm=float(grad_norm) if grad_norm is not None else 0.0, losses=tuple(host)))
 
-    def predict_price(self, inputs: Sequence[BlackScholes.Inputs]) -> list[float]:
-        """CVNN forward -> ifft -> mean -> real part = DC / N (reference :1709-1735)."""
+    def predict_price(self, inputs: Sequence[BlackScholes.Inputs]) -> Result[list[BlackScholes.HostPricingResults], PredictionFailed]:
+        """CVNN forward -> mean of the inverse DFT -> put price; call by parity (reference :1709-1769).
+        ``mean_n ifft(S)[n] == S[0] / N``, so the fused route needs no transform."""
+        if len(inputs) == 0:
+            return Success([])
         self._cvnn.eval()
         real_in, imag_in = _split_inputs(inputs, dtype=self._dtype, device=self._device)
-        if self._use_fused:
-            # mean_n ifft(S)[n] = S[0] / N: the price is the DC bin over N, no transform needed
-            fused = self._fused if self._fused is not None else FusedCVNN(self._cvnn)
-            self._fused = fused
-            pred_r, _ = fused.forward(real_in, imag_in)
-            return [float(x) for x in (pred_r[:, 0] / pred_r.shape[1]).cpu()]
-        with torch.no_grad():
-            pred_r, pred_i = self._cvnn(real_in, imag_in)
-            spectrum = torch.complex(pred_r, pred_i)
-            price = torch.fft.ifft(spectrum, dim=1).mean(dim=1).real
-        return [float(x) for x in price.cpu()]
+        try:
+            if self._use_fused:
+                if self._fused is None:
+                    self._fused = FusedCVNN(self._cvnn)
+                pred_r, pred_i = self._fused.forward(real_in, imag_in)
+                n = pred_r.shape[1]
+                coeffs = torch.stack((pred_r[:, 0] / n, pred_i[:, 0] / n), dim=1).cpu().tolist()
+            else:
+                with torch.no_grad():
+                    pred_r, pred_i = self._cvnn(real_in, imag_in)
+                    avg = torch.fft.ifft(torch.complex(pred_r, pred_i), dim=1).mean(dim=1)
+                coeffs = torch.stack((avg.real, avg.imag), dim=1).cpu().tolist()
+        except Exception as exc:  # noqa: BLE001 - mirrored from the reference (:1768)
+            return Failure(PredictionFailed(message=str(exc)))
+        out = []
+        for (real_val, imag_val), c in zip(coeffs, inputs):
+            if abs(imag_val) > 1.0e-6:
+                warnings.warn(f"IFFT imaginary component {imag_val:.3e} exceeds tolerance.", RuntimeWarning)
+            discount = math.exp(-c.r * c.T)
+            forward = c.X0 * math.exp((c.r - c.d) * c.T)
+            put, call = real_val, real_val + forward - c.K * discount
+            put_i, call_i = discount * max(c.K - forward, 0.0), discount * max(forward - c.K, 0.0)
+            out.append(BlackScholes.HostPricingResults(underlying=forward, put_price=put, call_price=call, put_price_intrinsic=put_i,
+                                                       call_price_intrinsic=call_i, put_convexity=put - put_i, call_convexity=call - call_i))
+        return Success(out)
 
-    def snapshot(self) -> PricerSnapshot:
+    # ------------------------------------------------------------------ checkpointing
+    def _current_optimizer_state(self) -> dict | None:
+        """Adam state in ``torch.optim.Adam.state_dict()`` layout (CPU) for both step routes."""
+        if self._use_fused and self._fused is not None and int(self._fused.step.item()) > 0:
+            return _to_cpu(self._fused.optimizer_state_dict())
+        return self._optimizer_state
+
+    def snapshot(self) -> Result[GbmCVNNPricerConfig, object]:
+        """Deterministic snapshot (reference :756-800): engine config with the advanced ``skip``,
+        Sobol position, step count, optimiser state, torch RNG states; ``cvnn`` is the live module
+        (clone it before training on, as the reference's tests do)."""
         cfg = self._engine.snapshot()
         if isinstance(cfg, Failure):
-            raise AssertionError(f"engine snapshot failed: {cfg.error}")
-        return PricerSnapshot(
-            cfg=cfg.value, sobol_skip=self._sobol_skip, global_step=self._global_step,
-            cvnn_state={k: v.detach().cpu().clone() for k, v in self._cvnn.state_dict().items()},
-            optimizer_state=self._optimizer_state(),
-        )
-
-    def _optimizer_state(self) -> dict | None:
-        """Adam state in ``torch.optim.Adam.state_dict()`` layout for both step routes."""
-        if self._use_fused:
-            return None if self._fused is None or int(self._fused.step.item()) == 0 else _to_cpu(self._fused.optimizer_state_dict())
-        return None if self._optimizer is None else _to_cpu(self._optimizer.state_dict())
-
-    @classmethod
-    def restore(cls, snap: PricerSnapshot, domain_bounds: DomainBounds, cvnn: nn.Module, *, learning_rate: float = 1e-2,
-                **kwargs) -> "GbmCVNNPricer":
-        cvnn.load_state_dict(snap.cvnn_state)
-        self = cls(snap.cfg, domain_bounds, cvnn, sobol_skip=snap.sobol_skip, global_step=snap.global_step, **kwargs)
-        if snap.optimizer_state is not None:
-            if self._use_fused:
-                self._fused = FusedCVNN(cvnn, lr=learning_rate)
-                self._fused.load_optimizer_state_dict(snap.optimizer_state)
-            else:
-                self._optimizer = optim.Adam(cvnn.parameters(), lr=learning_rate)
-                self._optimizer.load_state_dict(snap.optimizer_state)
-        return self
+            return cfg
+        cuda_rng = [s.cpu().numpy().tobytes() for s in torch.cuda.get_rng_state_all()] if torch.cuda.is_available() else None
+        return Success(GbmCVNNPricerConfig(cfg=cfg.value, domain_bounds=self._domain_bounds, cvnn=self._cvnn,
+                                           optimizer_state=self._current_optimizer_state(), global_step=self._global_step,
+                                           sobol_skip=self._sobol_skip, torch_cpu_rng_state=torch.get_rng_state().numpy().tobytes(),
+                                           torch_cuda_rng_states=cuda_rng))
 
 
 class _StepGraph:

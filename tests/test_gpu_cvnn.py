@@ -17,7 +17,7 @@ from oracle import cvnn as ocvnn
 from spectralmc_b200 import _cabi, cvnn
 from spectralmc_b200.effects import ForwardNormalization, PathScheme
 from spectralmc_b200.gbm import BlackScholes
-from spectralmc_b200.gbm_trainer import GbmCVNNPricer, TrainingConfig
+from spectralmc_b200.gbm_trainer import GbmCVNNPricer, TrainingConfig, build_gbm_cvnn_pricer_config
 from spectralmc_b200.numerical import Precision
 from tests.conftest import ROOT
 from tests.helpers import expect_success, make_black_scholes_config, make_domain_bounds, make_simulation_params
@@ -206,8 +206,8 @@ def _params(p):
 def test_graph_replay_is_bit_identical_to_eager_fused_steps(precision) -> None:
     a, b = _pricer(precision, cuda_graph=True), _pricer(precision, cuda_graph=False)
     assert a._use_fused and b._use_fused
-    la = expect_success(a.train(TrainingConfig(num_batches=4, batch_size=16)))
-    lb = expect_success(b.train(TrainingConfig(num_batches=4, batch_size=16)))
+    la = expect_success(a.train(TrainingConfig(num_batches=4, batch_size=16))).losses
+    lb = expect_success(b.train(TrainingConfig(num_batches=4, batch_size=16))).losses
     assert la == lb and len(a._graphs) == 1 and not b._graphs
     assert all(torch.equal(x, y) for x, y in zip(_params(a), _params(b)))
     # a second batch size captures a second graph; the first keeps working
@@ -221,19 +221,23 @@ def test_fused_training_tracks_the_torch_route(precision) -> None:
     """Same targets, same initial weights: the C-ABI step and the torch op-by-op step
     (GbmCVNNPricer._torch_step, reference gbm_trainer.py:819-835) stay together."""
     a, b = _pricer(precision), _pricer(precision, fused_step=False)
-    la = expect_success(a.train(TrainingConfig(num_batches=5, batch_size=32)))
-    lb = expect_success(b.train(TrainingConfig(num_batches=5, batch_size=32)))
+    ra = expect_success(a.train(TrainingConfig(num_batches=5, batch_size=32)))
+    rb = expect_success(b.train(TrainingConfig(num_batches=5, batch_size=32)))
+    la, lb = ra.losses, rb.losses
+    assert abs(ra.final_grad_norm - rb.final_grad_norm) <= (1e-9 if precision is Precision.float64 else 2e-3) * rb.final_grad_norm
     tol = 1e-9 if precision is Precision.float64 else 2e-3
     assert max(abs(x - y) / abs(y) for x, y in zip(la, lb)) <= tol
     assert max(nw(x, y) for x, y in zip(_params(a), _params(b))) <= tol
     # snapshots of the two routes are interchangeable (torch Adam state_dict layout)
-    sa, sb = a.snapshot(), b.snapshot()
+    sa, sb = expect_success(a.snapshot()), expect_success(b.snapshot())
     assert set(sa.optimizer_state["state"]) == set(sb.optimizer_state["state"])
-    c = GbmCVNNPricer.restore(sb, make_domain_bounds(), cvnn.make_cvnn(6, 16, seed=9, dtype=precision.to_torch()))
-    assert c._use_fused and int(c._fused.step.item()) == 5
-    lc = expect_success(c.train(TrainingConfig(num_batches=1, batch_size=32)))
-    ld = expect_success(b.train(TrainingConfig(num_batches=1, batch_size=32)))
-    assert abs(lc[0] - ld[0]) / abs(ld[0]) <= tol
+    import copy
+
+    c = expect_success(GbmCVNNPricer.create(sb.model_copy(update={"cvnn": copy.deepcopy(b._cvnn)})))  # torch-route snapshot -> fused trainer
+    assert c._use_fused
+    lc = expect_success(c.train(TrainingConfig(num_batches=1, batch_size=32))).losses
+    ld = expect_success(b.train(TrainingConfig(num_batches=1, batch_size=32))).losses
+    assert int(c._fused.step.item()) == 6 and abs(lc[0] - ld[0]) / abs(ld[0]) <= tol
 
 
 def test_learning_rate_change_recaptures_the_graph() -> None:
@@ -248,10 +252,14 @@ def test_predict_price_is_the_dc_bin_over_n() -> None:
     """mean_n ifft(S)[n] == S[0] / N (reference gbm_trainer.py:1729-1730)."""
     p = _pricer(Precision.float64)
     inputs = [BlackScholes.Inputs(X0=100, K=100, T=1.0, r=0.05, d=0.0, v=0.2), BlackScholes.Inputs(X0=50, K=60, T=0.5, r=0.0, d=0.0, v=0.4)]
-    fused = p.predict_price(inputs)
-    q = _pricer(Precision.float64, fused_step=False)
-    generic = q.predict_price(inputs)
-    assert max(abs(x - y) / abs(y) for x, y in zip(fused, generic)) <= 1e-12
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        fused = expect_success(p.predict_price(inputs))
+        generic = expect_success(_pricer(Precision.float64, fused_step=False).predict_price(inputs))
+    for x, y in zip(fused, generic):
+        assert abs(x.put_price - y.put_price) <= 1e-12 * abs(y.put_price) and abs(x.call_price - y.call_price) <= 1e-12 * abs(y.call_price)
 
 
 def test_unsupported_networks_take_the_torch_route() -> None:

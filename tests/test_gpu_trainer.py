@@ -4,7 +4,9 @@ train / snapshot / restore) and the prediction smoke test (:302-320)."""
 
 from __future__ import annotations
 
+import copy
 import math
+import warnings
 
 import numpy as np
 import pytest
@@ -16,47 +18,145 @@ from oracle.sobol import sobol_contracts
 from spectralmc_b200.cvnn import make_cvnn
 from spectralmc_b200.effects import ForwardNormalization, PathScheme
 from spectralmc_b200.gbm import BlackScholes
-from spectralmc_b200.gbm_trainer import GbmCVNNPricer, TrainingConfig, _split_inputs
+from spectralmc_b200.gbm_trainer import (
+    GbmCVNNPricer,
+    _split_inputs,
+    build_gbm_cvnn_pricer_config,
+    build_training_config,
+)
 from spectralmc_b200.numerical import Precision
-from tests.helpers import expect_success, make_black_scholes_config, make_domain_bounds, make_simulation_params, rel_max
+from tests.helpers import expect_failure, expect_success, make_black_scholes_config, make_domain_bounds, make_simulation_params, rel_max
 
 pytestmark = pytest.mark.gpu
 
 
-def _pricer(precision=Precision.float32, *, seed=42, N=16, B=2**12, T=1, norm=ForwardNormalization.RAW):
+LEARNING_RATE = 1.0e-2  # the reference's tests/test_gbm_trainer.py:70
+PRECISIONS = (Precision.float32, Precision.float64)
+
+
+def _pricer(precision=Precision.float32, *, seed=42, N=16, B=2**12, T=1, norm=ForwardNormalization.RAW, **kw):
+    """The reference's ``_make_gbm_trainer`` (tests/test_gbm_trainer.py:122-162)."""
     sp = make_simulation_params(timesteps=T, network_size=N, batches_per_mc_run=B, threads_per_block=256, mc_seed=seed,
                                 buffer_size=1, dtype=precision)
     cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=norm)
-    cvnn = make_cvnn(6, N, seed=seed, dtype=precision.to_torch())
-    return GbmCVNNPricer(cfg, make_domain_bounds(), cvnn)
+    net = make_cvnn(6, N, seed=seed, dtype=precision.to_torch())
+    pricer_cfg = expect_success(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=net))
+    return expect_success(GbmCVNNPricer.create(pricer_cfg, **kw))
+
+
+def _tc(num_batches, batch_size=8, learning_rate=LEARNING_RATE):
+    return expect_success(build_training_config(num_batches=num_batches, batch_size=batch_size, learning_rate=learning_rate))
 
 
 def _max_param_diff(a, b) -> float:
-    return max(float((p - q).abs().max()) for p, q in zip(a._cvnn.parameters(), b._cvnn.parameters()))
+    return max(float((p.detach() - q.detach()).abs().max()) for p, q in zip(a._cvnn.parameters(), b._cvnn.parameters()))
 
 
-@pytest.mark.parametrize("precision", [Precision.float32, Precision.float64])
+def _clone_model(model):
+    return copy.deepcopy(model)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_deterministic_construction(precision) -> None:
+    assert _max_param_diff(_pricer(precision), _pricer(precision)) == 0.0
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_lockstep_training(precision) -> None:
-    a, b = _pricer(precision), _pricer(precision)
-    la = expect_success(a.train(TrainingConfig(num_batches=3, batch_size=8)))
-    lb = expect_success(b.train(TrainingConfig(num_batches=3, batch_size=8)))
-    assert la == lb and all(math.isfinite(x) for x in la)
-    assert _max_param_diff(a, b) == 0.0
-    sa, sb = a.snapshot(), b.snapshot()
-    assert sa.sobol_skip == sb.sobol_skip == 24 and sa.global_step == 3
-    assert sa.cfg.sim_params.skip == 24  # one normal matrix per contract priced
+    """tests/test_gbm_trainer.py:182-195: two trainers stay bit-identical through several train() calls."""
+    a, b = _pricer(precision, seed=43), _pricer(precision, seed=43)
+    for batches in (2, 3, 1):
+        ra, rb = expect_success(a.train(_tc(batches))), expect_success(b.train(_tc(batches)))
+        assert ra.losses == rb.losses and all(math.isfinite(x) for x in ra.losses)
+        assert ra.total_batches == batches and ra.final_loss == ra.losses[-1] and math.isfinite(ra.final_grad_norm)
+        assert _max_param_diff(a, b) == 0.0
+    sa, sb = expect_success(a.snapshot()), expect_success(b.snapshot())
+    assert sa.sobol_skip == sb.sobol_skip == 48 and sa.global_step == 6
+    assert sa.cfg.sim_params.skip == 48  # one normal matrix per contract priced
 
 
-def test_snapshot_cycle_deterministic() -> None:
-    """train 2 -> snapshot -> train 2 more  ==  restore(snapshot) -> train 2."""
-    a = _pricer()
-    expect_success(a.train(TrainingConfig(num_batches=2, batch_size=8)))
-    snap = a.snapshot()
-    expect_success(a.train(TrainingConfig(num_batches=2, batch_size=8)))
-    b = GbmCVNNPricer.restore(snap, make_domain_bounds(), make_cvnn(6, 16, seed=1))
-    expect_success(b.train(TrainingConfig(num_batches=2, batch_size=8)))
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_snapshot_cycle_deterministic(precision) -> None:
+    """tests/test_gbm_trainer.py:203-223: train 3 -> snapshot -> clone; both train 2 more."""
+    trainer = _pricer(precision, seed=44)
+    expect_success(trainer.train(_tc(3)))
+    snap = expect_success(trainer.snapshot()).model_copy(update={"cvnn": _clone_model(trainer._cvnn)})
+    clone = expect_success(GbmCVNNPricer.create(snap))
+    expect_success(trainer.train(_tc(2)))
+    expect_success(clone.train(_tc(2)))
+    assert _max_param_diff(trainer, clone) == 0.0
+    done = expect_success(clone.snapshot())
+    assert done.global_step == 5 and done.sobol_skip == 40 and done.cfg.sim_params.skip == 40
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_snapshot_restart_without_optimizer(precision) -> None:
+    """tests/test_gbm_trainer.py:231-263."""
+    def restarted_without_optimizer():
+        t = _pricer(precision, seed=45)
+        expect_success(t.train(_tc(3)))
+        snap = expect_success(t.snapshot()).model_copy(update={"optimizer_state": None, "cvnn": _clone_model(t._cvnn)})
+        return expect_success(GbmCVNNPricer.create(snap))
+
+    a, b = restarted_without_optimizer(), restarted_without_optimizer()
+    expect_success(a.train(_tc(2)))
+    expect_success(b.train(_tc(2)))
     assert _max_param_diff(a, b) == 0.0
-    assert b.snapshot().global_step == 4 and b.snapshot().sobol_skip == 32
+    assert float(expect_success(a.snapshot()).optimizer_state["state"][0]["step"]) == 2.0  # Adam restarted from zero
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_snapshot_optimizer_state_layout(precision) -> None:
+    """tests/test_gbm_trainer.py:271-296: the snapshot carries Adam's state for every parameter, on the CPU."""
+    trainer = _pricer(precision, seed=50)
+    expect_success(trainer.train(_tc(4)))
+    opt = expect_success(trainer.snapshot()).optimizer_state
+    assert opt is not None and len(opt["param_groups"]) == 1 and len(opt["state"]) == len(list(trainer._cvnn.parameters()))
+    for entry in opt["state"].values():
+        assert float(entry["step"]) == 4.0 and entry["exp_avg"].device.type == "cpu" and entry["exp_avg_sq"].device.type == "cpu"
+    reference_adam = torch.optim.Adam(_clone_model(trainer._cvnn).parameters(), lr=LEARNING_RATE)
+    reference_adam.load_state_dict(opt)  # the layout IS torch.optim.Adam's
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_predict_price_smoke(precision) -> None:
+    """tests/test_gbm_trainer.py:304-320."""
+    trainer = _pricer(precision, seed=60)
+    expect_success(trainer.train(_tc(1, batch_size=4)))
+    contracts = [BlackScholes.Inputs(X0=100.0, K=100.0, T=1.0, r=0.05, d=0.02, v=0.20),
+                 BlackScholes.Inputs(X0=120.0, K=110.0, T=0.5, r=0.03, d=0.01, v=0.25)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)  # an untrained network's DC bin need not be real
+        results = expect_success(trainer.predict_price(contracts))
+    assert len(results) == len(contracts)
+    for res in results:
+        for val in res.model_dump(mode="python").values():
+            assert isinstance(val, float) and math.isfinite(val)
+    assert expect_success(trainer.predict_price([])) == []
+
+
+def test_step_logger_receives_every_step() -> None:
+    """The ``logger`` callback of train() (reference :1567-1583)."""
+    seen = []
+    trainer = _pricer(seed=7)
+    result = expect_success(trainer.train(_tc(3), logger=seen.append))
+    assert [m.step for m in seen] == [1, 2, 3] and [m.loss for m in seen] == list(result.losses)
+    assert all(m.lr == LEARNING_RATE and math.isfinite(m.grad_norm) and m.grad_norm > 0 and m.model is trainer._cvnn for m in seen)
+    assert seen[-1].grad_norm == result.final_grad_norm
+
+
+def test_training_config_and_device_validation() -> None:
+    from spectralmc_b200.errors import DeviceDTypeError, DeviceNotCUDA, InvalidTrainingConfig
+
+    for bad in (dict(num_batches=0, batch_size=8, learning_rate=0.01), dict(num_batches=1, batch_size=0, learning_rate=0.01),
+                dict(num_batches=1, batch_size=8, learning_rate=1.0), dict(num_batches=1, batch_size=8, learning_rate=0.0)):
+        assert isinstance(expect_failure(build_training_config(**bad)), InvalidTrainingConfig)
+    sp = make_simulation_params(timesteps=1, network_size=16, batches_per_mc_run=64, mc_seed=3, dtype=Precision.float32)
+    cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+    on_cpu = expect_success(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=make_cvnn(6, 16, device="cpu")))
+    assert isinstance(expect_failure(GbmCVNNPricer.create(on_cpu)), DeviceNotCUDA)
+    wrong = expect_success(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=make_cvnn(6, 16, dtype=torch.float64)))
+    assert isinstance(expect_failure(GbmCVNNPricer.create(wrong)), DeviceDTypeError)
 
 
 def test_targets_match_oracle_for_a_sobol_batch() -> None:
@@ -76,11 +176,13 @@ def test_split_inputs_and_predict_price_smoke() -> None:
     inputs = [BlackScholes.Inputs(X0=100, K=100, T=1.0, r=0.05, d=0.0, v=0.2), BlackScholes.Inputs(X0=50, K=60, T=0.5, r=0.0, d=0.0, v=0.4)]
     real, imag = _split_inputs(inputs, dtype=torch.float32, device=torch.device("cuda"))
     assert real.shape == (2, 6) and float(real[1, 1]) == 60.0 and float(imag.abs().max()) == 0.0
-    prices = p.predict_price(inputs)
-    assert len(prices) == 2 and all(math.isfinite(x) for x in prices)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        prices = expect_success(p.predict_price(inputs))
+    assert len(prices) == 2 and all(math.isfinite(x.put_price) for x in prices)
 
 
 def test_training_reduces_the_loss() -> None:
     p = _pricer(Precision.float32, N=16, B=2**10)
-    losses = expect_success(p.train(TrainingConfig(num_batches=30, batch_size=32, learning_rate=1e-2)))
+    losses = expect_success(p.train(_tc(30, batch_size=32))).losses
     assert np.mean(losses[-5:]) < np.mean(losses[:5])

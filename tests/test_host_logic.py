@@ -117,3 +117,40 @@ def test_sobol_bounds_and_validation() -> None:
     neg = expect_success(SobolSampler.create(BlackScholes.Inputs, make_domain_bounds(x0=(-5.0, -1.0)), config=SobolConfig(seed=1)))
     assert "SamplerValidationFailed" in str(expect_failure(neg.sample(4)))
     assert "SamplerValidationFailed" in str(expect_failure(neg.sample_array(4)))
+
+
+def test_training_config_validation_mirrors_the_reference() -> None:
+    """gbm_trainer.py:261-298 — positive counts, learning rate in (0, 1); no device needed."""
+    from spectralmc_b200.errors import InvalidTrainingConfig
+    from spectralmc_b200.gbm_trainer import TrainingConfig, build_training_config
+
+    ok = build_training_config(num_batches=3, batch_size=8, learning_rate=1e-2)
+    assert isinstance(ok, Success) and ok.value == TrainingConfig(num_batches=3, batch_size=8, learning_rate=1e-2)
+    for bad, word in ((dict(num_batches=0, batch_size=8, learning_rate=0.01), "num_batches"),
+                      (dict(num_batches=1, batch_size=-1, learning_rate=0.01), "batch_size"),
+                      (dict(num_batches=1, batch_size=8, learning_rate=1.0), "learning_rate"),
+                      (dict(num_batches=1, batch_size=8, learning_rate=0.0), "learning_rate")):
+        got = build_training_config(**bad)
+        assert isinstance(got, Failure) and isinstance(got.error, InvalidTrainingConfig) and word in got.error.message
+
+
+def test_pricer_create_rejects_a_cpu_model_without_touching_the_device() -> None:
+    """gbm_trainer.py:600-640 — DeviceNotCUDA / DeviceDTypeError are decided from the module's tensors."""
+    import torch
+
+    from spectralmc_b200.cvnn import make_cvnn
+    from spectralmc_b200.errors import DeviceDTypeError, DeviceNotCUDA
+    from spectralmc_b200.gbm_trainer import GbmCVNNPricer, build_gbm_cvnn_pricer_config
+    from tests.helpers import make_black_scholes_config, make_domain_bounds, make_simulation_params
+
+    sp = make_simulation_params(timesteps=1, network_size=16, batches_per_mc_run=64, mc_seed=3)
+    cfg = make_black_scholes_config(sim_params=sp)
+    pc = build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=make_cvnn(6, 16, device="cpu"))
+    assert isinstance(pc, Success) and pc.value.global_step == 0 and pc.value.optimizer_state is None
+    got = GbmCVNNPricer.create(pc.value)
+    assert isinstance(got, Failure) and isinstance(got.error, DeviceNotCUDA)
+    mixed = make_cvnn(6, 16, device="cpu")
+    mixed.layers[1].double()
+    got = GbmCVNNPricer.create(pc.value.model_copy(update={"cvnn": mixed}))
+    assert isinstance(got, Failure) and isinstance(got.error, DeviceDTypeError)
+    assert isinstance(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=mixed, bogus=1), Failure)

@@ -82,7 +82,7 @@ for name, T, N, B, steps in (("c3 training step, trainer-test size (T=1,N=16,B=4
     pricer.train(TrainingConfig(num_batches=1, batch_size=1024)).unwrap()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    losses = pricer.train(TrainingConfig(num_batches=steps, batch_size=1024)).unwrap()
+    losses = pricer.train(TrainingConfig(num_batches=steps, batch_size=1024)).unwrap().losses
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / steps
     print(json.dumps({"what": name, "ms_per_training_step": dt * 1e3, "contracts_per_step": 1024, "cf_estimates_per_sec": 1024 / dt,

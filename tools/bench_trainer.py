@@ -38,7 +38,7 @@ for T, N, B in ((1, 16, 4096), (16, 128, 1024)):
         best = float("inf")
         for _ in range(3):
             t0 = time.perf_counter()
-            losses = pricer.train(TrainingConfig(num_batches=steps, batch_size=1024)).unwrap()
+            losses = pricer.train(TrainingConfig(num_batches=steps, batch_size=1024)).unwrap().losses
             torch.cuda.synchronize()
             best = min(best, (time.perf_counter() - t0) / steps)
         # device-only time of the CVNN step (no simulation), CUDA events

@@ -21,5 +21,5 @@ sp = SimulationParams(timesteps=1, network_size=N, batches_per_mc_run=4096, thre
                       dtype=Precision.float32)
 cfg = BlackScholesConfig(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
 pricer = GbmCVNNPricer(cfg, bounds, make_cvnn(6, N, seed=42), cuda_graph=False)
-print(pricer.train(TrainingConfig(num_batches=4, batch_size=1024)).unwrap())
+print(pricer.train(TrainingConfig(num_batches=4, batch_size=1024)).unwrap().losses)
 torch.cuda.synchronize()
