@@ -280,10 +280,14 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
   constexpr int kUnroll = SMC_F64_UNROLL;
 #pragma unroll kUnroll
   for (uint32_t q = 0; q < nq; ++q) {
-    double z[2];
-    normals2_f64(col, q, k_lo, k_hi, keys, z);
-    consume<double, SCHEME>(acc, z[0], k);
-    consume<double, SCHEME>(acc, z[1], k);
+    if (SCHEME == SMC_LOG_EULER) {
+      acc = normals2_sum_f64(col, q, k_lo, k_hi, keys, acc);
+    } else {
+      double z[2];
+      normals2_f64(col, q, k_lo, k_hi, keys, z);
+      consume<double, SCHEME>(acc, z[0], k);
+      consume<double, SCHEME>(acc, z[1], k);
+    }
   }
   if (timesteps & 1) {
     double z[2];

@@ -268,6 +268,31 @@ static __constant__ double kLogCoef[7] = {6.666666666666735130e-01, 3.9999999999
 static __constant__ double kLogMisc[4] = {6.93147180369123816490e-01 /* ln2 hi */, 1.90821492927058770002e-10 /* ln2 lo */,
                                           3.14159265358979311600e+00 /* pi hi */, 1.22464679914735317723e-16 /* pi lo */};
 
+// Division and square root for the well-scaled positive arguments Box–Muller produces (no zero,
+// subnormal, infinite or NaN input can occur), from the MUFU seeds (RCP64H / RSQ64H, relative error
+// 2^-22) and FP64 Newton steps.  The compiler's general-purpose sequences carry a range test, a branch
+// and an out-of-line slow path per call (12 of the 113 non-FP64 issue slots of the float64 loop);
+// the results here are within 1 ulp (tests/test_gpu_normals.py holds the stream to 1e-13).
+__device__ __forceinline__ double div_pos_f64(double a, double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  e = fma(e, e, e);                       // e + e^2
+  r = fma(r, e, r);                       // r (1 + e + e^2): relative error 2^-66
+  const double q = a * r;
+  return fma(fma(-d, q, a), r, q);        // one residual correction
+}
+__device__ __forceinline__ double sqrt_pos_f64(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x * y, y, 1.0);            // 1 - x y^2
+  y = fma(y * e, fma(e, 0.375, 0.5), y);           // y (1 + e/2 + 3 e^2 / 8)
+  const double g = x * y;
+  return fma(fma(-g, g, x), 0.5 * y, g);           // g + (x - g^2) / (2 g)
+}
+
+static __constant__ double kLogMisc2[2] = {2.0, 0x1p-52};  // angle / pi = 2 w + 2^-52 with constant-bank operands
+
 // natural log of u in (0, 1), u normal
 __device__ __forceinline__ double log_unit_interval(double u) {
   int hi = __double2hiint(u);
@@ -279,7 +304,7 @@ __device__ __forceinline__ double log_unit_interval(double u) {
     k += 1;
   }
   const double f = __hiloint2double(hi, lo) - 1.0;
-  const double s = f / (2.0 + f);
+  const double s = div_pos_f64(f, 2.0 + f);
   const double z = s * s, w = z * z;
   const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
   const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
@@ -303,6 +328,45 @@ __device__ __forceinline__ void sincospi_unit(double t, double& sn, double& cs) 
   cs = ((q + 1) & 2) ? -b : b;                 // q: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
 }
 
+// sin(pi t) + cos(pi t) with the quadrant signs folded in by XOR on the high words (no selects):
+// with n = rint(2 t), q = n mod 4 and (s0, c0) = (sin, cos)(pi (t - n/2)):
+//   cos(pi t) + sin(pi t) = sigma_c c0 + sigma_s s0,  sigma_c = -1 iff q in {2,3},  sigma_s = -1 iff q in {1,2}
+// (the two terms swap roles for odd q, which a SUM does not see).  Returned separately so the caller
+// can keep two FMAs into its accumulator: acc += r * c_term; acc += r * s_term.
+__device__ __forceinline__ void sincospi_unit_terms(double t, double& c_term, double& s_term) {
+  const double n = rint(2.0 * t);
+  const double r = fma(n, -0.5, t);
+  const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);
+  const double z = x * x;
+  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
+  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);
+  const double s0 = fma(x * z, ps, x);
+  const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+  const uint32_t q = static_cast<uint32_t>(static_cast<int>(n));
+  const uint32_t flip_c = (q << 30) & 0x80000000u;               // bit 1 of q
+  const uint32_t flip_s = ((q ^ (q >> 1)) << 31);                // bit 0 of q xor bit 1 of q
+  c_term = __hiloint2double(__double2hiint(c0) ^ static_cast<int>(flip_c), __double2loint(c0));
+  s_term = __hiloint2double(__double2hiint(s0) ^ static_cast<int>(flip_s), __double2loint(s0));
+}
+
+// acc + z[0] + z[1] of normals2_f64 (same draws; for the log-Euler sum, where the order of the two
+// normals of a pair does not matter)
+__device__ __forceinline__ double normals2_sum_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                                   const PhiloxKeys& key, double acc) {
+  uint32_t x[4];
+  philox4x32_10(col, q, k_lo, k_hi | F64_STREAM_BIT, key, x);
+  const double u1 =
+      __hiloint2double(static_cast<int>((x[0] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[1])) -
+      0x1.fffffffffffffp-1;
+  const double w =
+      __hiloint2double(static_cast<int>((x[2] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[3])) - 1.5;
+  const double r = sqrt_pos_f64(-2.0 * log_unit_interval(u1));
+  double ct, st;
+  sincospi_unit_terms(fma(w, kLogMisc2[0], kLogMisc2[1]), ct, st);
+  acc = fma(r, ct, acc);
+  return fma(r, st, acc);
+}
+
 __device__ __forceinline__ void normals2_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                              const PhiloxKeys& key, double (&z)[2]) {
   uint32_t x[4];
@@ -314,9 +378,9 @@ __device__ __forceinline__ void normals2_f64(uint32_t col, uint32_t q, uint32_t 
   const double w =
       __hiloint2double(static_cast<int>((x[2] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[3])) -
       1.5;  // u2 - 0.5 - 2^-53
-  const double r = sqrt(-2.0 * log_unit_interval(u1));
+  const double r = sqrt_pos_f64(-2.0 * log_unit_interval(u1));
   double s, c;
-  sincospi_unit(2.0 * w + 0x1p-52, s, c);  // angle / pi = 2 (u2 - 0.5), exact
+  sincospi_unit(fma(w, kLogMisc2[0], kLogMisc2[1]), s, c);  // angle / pi = 2 (u2 - 0.5), exact
   z[0] = r * c;
   z[1] = r * s;
 }

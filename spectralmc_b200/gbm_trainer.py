@@ -277,16 +277,18 @@ class GbmCVNNPricer:
                 return Failure(SamplerInitFailed(error=drawn.error))
             self._sobol_skip += config.batch_size
             contracts = self._upload(drawn.value)
-            got = self.targets(contracts)
+            with _nvtx("smc.targets"):  # visible in ncu / nsys timelines (the reference has no profiler hooks)
+                got = self.targets(contracts)
             if isinstance(got, Failure):
                 return got
             targets = got.value.detach()  # already a torch tensor: the DLPack hand-off is the identity
-            if self._use_fused:
-                self._fused_step(contracts, targets, losses[i : i + 1])
-            else:
-                real_in = contracts.to(self._dtype)
-                loss, grad_norm = self._torch_step(real_in, torch.zeros_like(real_in), targets, optimizer)
-                losses[i : i + 1].copy_(loss.detach())
+            with _nvtx("smc.cvnn_step"):
+                if self._use_fused:
+                    self._fused_step(contracts, targets, losses[i : i + 1])
+                else:
+                    real_in = contracts.to(self._dtype)
+                    loss, grad_norm = self._torch_step(real_in, torch.zeros_like(real_in), targets, optimizer)
+                    losses[i : i + 1].copy_(loss.detach())
             self._global_step += 1
             if logger is not None:  # per-step host metrics, as the reference produces them (:1567-1583)
                 gn = self._fused.grads.norm() if self._use_fused else grad_norm
@@ -371,6 +373,19 @@ class _StepGraph:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             fused.train_step(self.real_in, self.imag_in, self.targets, self.loss)
+
+
+class _nvtx:
+    """NVTX range around a phase of the training step."""
+
+    def __init__(self, name: str) -> None:
+        self.name = name
+
+    def __enter__(self) -> None:
+        torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc) -> None:
+        torch.cuda.nvtx.range_pop()
 
 
 def _to_cpu(obj):

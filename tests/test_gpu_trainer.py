@@ -186,3 +186,25 @@ def test_training_reduces_the_loss() -> None:
     p = _pricer(Precision.float32, N=16, B=2**10)
     losses = expect_success(p.train(_tc(30, batch_size=32))).losses
     assert np.mean(losses[-5:]) < np.mean(losses[:5])
+
+
+def test_full_stack_normalize_train_snapshot_reload_predict() -> None:
+    """The reference's end-to-end test without its S3 store (tests/test_e2e/test_full_stack_cvnn_pricer.py:41-125):
+    16 steps x 128 x 4 batches with the default NORMALIZE, train 4 x 8, snapshot, rebuild, predict."""
+    trainer = _pricer(Precision.float32, seed=11, N=128, B=4, T=16, norm=ForwardNormalization.NORMALIZE)
+    result = expect_success(trainer.train(_tc(4, batch_size=8)))
+    assert result.total_batches == 4 and all(math.isfinite(x) for x in result.losses)
+    snap = result.updated_config
+    assert snap.global_step == 4 and snap.sobol_skip == 32 and snap.cfg.sim_params.skip == 32
+    assert snap.cfg.normalization is ForwardNormalization.NORMALIZE
+    reloaded = expect_success(GbmCVNNPricer.create(snap.model_copy(update={"cvnn": _clone_model(trainer._cvnn)})))
+    contracts = [BlackScholes.Inputs(X0=100.0, K=100.0, T=1.0, r=0.05, d=0.02, v=0.20)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        a = expect_success(trainer.predict_price(contracts))[0]
+        b = expect_success(reloaded.predict_price(contracts))[0]
+    assert a == b and math.isfinite(a.put_price)
+    # and the reloaded trainer continues exactly where the original would
+    expect_success(trainer.train(_tc(1, batch_size=8)))
+    expect_success(reloaded.train(_tc(1, batch_size=8)))
+    assert _max_param_diff(trainer, reloaded) == 0.0
