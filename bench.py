@@ -43,6 +43,8 @@ WORKLOADS = {
     "c2x8": dict(contracts=8, T=252, N=128, B=65536, dtype="float32"),
     "c3_trainer": dict(contracts=1024, T=1, N=16, B=4096, dtype="float32"),
     "c4": dict(contracts=512, T=365, N=256, B=4096, dtype="float64"),
+    # BASELINE configs[4] on 8 GPUs: 4096 contracts x 2^20 batch rows (131 072 per GPU), 1.39e14 path-steps per step
+    "c5": dict(contracts=4096, T=252, N=128, B=131072, dtype="float32"),
 }
 # SASS-counted work per fp32 path-step of the fused log-Euler kernel (profiles/ has the listing):
 ISSUE_SLOTS_PER_STEP = 163.0 / 12.0  # warp-instructions issued per path-step per lane (163 per two 6-normal blocks, SASS: profiles/r1_fused_f32_sass_inner_loop.txt)
