@@ -292,8 +292,8 @@ def run_b200(args) -> None:
             "peak": (calib["ffma"] if bound == "fp32_issue" else calib["mufu"]) / 1e12,
             "unit": "Tlane-op/s", "frac": max(fr_issue, fr_xu),
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full` launch at this
-            # workload (profiles/r1_fused_f32_ncu_raw.csv): 22 528 B read, 0 B written; algorithmic input 48 B
-            "traffic": 22528 if args.workload == "c2" else None,
+            # workload (profiles/r1_fused_f32_ncu_raw.csv): 23 808 B read, 4 096 B written; algorithmic input 48 B
+            "traffic": 27904 if args.workload == "c2" else None,
             "peak_source": "calibrated live: smc_pipe_calibrate (FFMA issue-rate and MUFU.EX2 microbenchmarks); MEASURED_PEAKS.json holds only HBM/bf16",
             "detail": {"issue_slots_per_path_step": ISSUE_SLOTS_PER_STEP, "xu_ops_per_path_step": XU_OPS_PER_STEP,
                        "fp32_issue": {"achieved": issue_ach / 1e12, "peak": calib["ffma"] / 1e12, "frac": fr_issue},
