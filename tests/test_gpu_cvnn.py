@@ -278,3 +278,22 @@ def test_unsupported_networks_take_the_torch_route() -> None:
     expect_success(p.train(TrainingConfig(num_batches=1, batch_size=8)))
     with pytest.raises(ValueError):
         GbmCVNNPricer(cfg, make_domain_bounds(), Odd(), fused_step=True)
+
+
+def test_wide_network_and_large_batch() -> None:
+    """Sizes beyond the reference's tests: 20 000 rows (157 column-sum slabs, 256 weight-gradient splits
+    capped), hidden width 256, 128 outputs."""
+    layers = [("linear", 6, 256, True), ("modrelu", 256), ("linear", 256, 128, True)]
+    torch.manual_seed(5)
+    net = build(layers, torch.float32)
+    rows = 20000
+    real, imag = torch.randn(rows, 6, device=DEV), torch.randn(rows, 6, device=DEV)
+    ref_r, ref_i = net(real, imag)
+    targets = torch.complex(torch.randn_like(ref_r), torch.randn_like(ref_r))
+    ref_loss = torch.nn.functional.mse_loss(ref_r, targets.real) + torch.nn.functional.mse_loss(ref_i, targets.imag)
+    ref_grads = torch.autograd.grad(ref_loss, list(net.parameters()))
+    fused = cvnn.FusedCVNN(net)
+    loss = fused.loss_backward(real, imag, targets)
+    assert abs(float(loss) - float(ref_loss.detach())) <= 1e-5 * float(ref_loss.detach())
+    for p, g in zip(net.parameters(), ref_grads):
+        assert nw(p.grad, g) <= 1e-4
