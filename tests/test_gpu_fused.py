@@ -23,8 +23,9 @@ from oracle.black76 import black76
 from oracle.sobol import sobol_contracts
 from spectralmc_b200 import _cabi
 from spectralmc_b200.effects import ForwardNormalization, PathScheme
-from spectralmc_b200.gbm import BlackScholes
+from spectralmc_b200.gbm import BlackScholes, build_simulation_params
 from spectralmc_b200.numerical import Precision
+from spectralmc_b200.result import Failure
 from tests.helpers import expect_success, make_black_scholes_config, make_simulation_params, rel_max
 
 pytestmark = pytest.mark.gpu
@@ -307,3 +308,41 @@ def test_baseline_config_c4_against_black76() -> None:
     assert float(np.mean(z > 3.0)) <= 0.05, np.sort(z)[-8:]
     assert float(np.sqrt(np.mean(((mean - analytic) / analytic)[big] ** 2))) <= 0.15
     assert expect_success(engine.snapshot()).sim_params.skip == 8 * 512
+
+
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+def test_top_of_the_32_bit_path_counter(prec) -> None:
+    """Maximum sizes: the ABI admits batches_total * N <= 2^32 - 1 global paths.  A rank that owns the
+    LAST batch rows of such a job draws counters just below 2^32; its partial CF equals the oracle's
+    on the same column slice (no wrap-around, no sign trouble in the 64-bit index arithmetic)."""
+    dtype, np_dtype = (torch.float64, np.float64) if prec == "float64" else (torch.float32, np.float32)
+    T, N = 7, 64
+    B_total = 2**26 - 1  # 64 * (2^26 - 1) = 2^32 - 64 paths
+    rows_local = 8
+    b0 = B_total - rows_local
+    got = _fused([CANON, ODD], T, N, B_total, dtype, 42, 3, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, batch_begin=b0, batch_end=B_total)
+    for i, row in enumerate((CANON, ODD)):
+        z = philox.normals_matrix(T, N * B_total, np_dtype, 42, 3 + i, col_begin=b0 * N, col_end=B_total * N)
+        cf, _ = ogbm.simulate_fft(ogbm.Contract(*row), z, N, scheme="log_euler", normalization=ogbm.RAW)
+        ref = np.asarray(cf, dtype=np.complex128) * (rows_local / B_total)  # partial: (1 / B_total) * sum over local rows
+        assert rel_max(got[i], ref) <= (1e-12 if prec == "float64" else 1e-5)
+    # one more row would pass 2^32 - 1 paths: rejected with a message, nothing launched
+    contracts = torch.tensor([CANON], dtype=torch.float64, device="cuda")
+    args = _cabi.make_fused_args(contracts, 1, T, N, 2**26, dtype, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 42, 0, batch_begin=0, batch_end=8)
+    with pytest.raises(_cabi.SmcError) as err:
+        _cabi.cf_fused(args, contracts.device, dtype)
+    assert err.value.code == 1 and "32-bit path counter" in err.value.message
+
+
+def test_engine_at_the_reference_memory_guard() -> None:
+    """The reference's soft cap (gbm.py:123-137): 1e9 float32 paths per contract.  The fused path never
+    materialises them, so a full-guard contract is one ordinary call: N = 1000 (table DFT), B = 10^6, T = 1."""
+    engine = _engine(Precision.float32, T=1, N=1000, B=1_000_000, seed=5)
+    cf = expect_success(engine.simulate_fft(BlackScholes.Inputs(X0=100, K=100, T=1.0, r=0.05, d=0.0, v=0.2))).cpu().numpy()
+    ref = black76(*CANON)["put_price"]
+    se = 7.2 / math.sqrt(1e9)
+    assert cf.shape == (1000,) and abs(cf[0].real / 1000 - ref) <= 5 * se + 2e-5 * ref and cf[0].imag == 0.0
+    assert np.max(np.abs(cf[1:] - np.conj(cf[1:][::-1]))) <= 1e-5 * abs(cf[0])
+    too_big = build_simulation_params(timesteps=1, network_size=1001, batches_per_mc_run=1_000_000, threads_per_block=256,
+                                      mc_seed=5, buffer_size=1, dtype=Precision.float32)
+    assert isinstance(too_big, Failure)
