@@ -61,3 +61,54 @@ def test_two_gpu_sharding_matches_single_gpu(prec, norm) -> None:
     for rank, sharded, whole in results:
         assert np.max(np.abs(sharded - whole)) <= tol * np.max(np.abs(whole)), rank
     assert np.array_equal(results[0][1], results[1][1])
+
+
+def _train_worker(rank: int, world: int, port: int, queue) -> None:
+    import torch.distributed as dist
+
+    from spectralmc_b200.cvnn import make_cvnn
+    from spectralmc_b200.effects import ForwardNormalization, PathScheme
+    from spectralmc_b200.gbm_trainer import GbmCVNNPricer, build_gbm_cvnn_pricer_config, build_training_config
+    from spectralmc_b200.numerical import Precision
+    from tests.helpers import expect_success, make_black_scholes_config, make_domain_bounds, make_simulation_params
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        sp = make_simulation_params(timesteps=4, network_size=16, batches_per_mc_run=1024, mc_seed=9, dtype=Precision.float32)
+        cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+        net = make_cvnn(6, 16, seed=9, device=f"cuda:{rank}")
+        pc = expect_success(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=net))
+        trainer = expect_success(GbmCVNNPricer.create(pc, process_group=dist.group.WORLD))
+        result = expect_success(trainer.train(expect_success(build_training_config(num_batches=3, batch_size=16, learning_rate=1e-2))))
+        single = expect_success(GbmCVNNPricer.create(expect_success(build_gbm_cvnn_pricer_config(
+            cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=make_cvnn(6, 16, seed=9, device=f"cuda:{rank}")))))
+        alone = expect_success(single.train(expect_success(build_training_config(num_batches=3, batch_size=16, learning_rate=1e-2))))
+        torch.cuda.synchronize()
+        queue.put((rank, result.losses, alone.losses, [p.detach().cpu().numpy() for p in net.parameters()]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_training_replicas_stay_identical() -> None:
+    """Batch rows sharded over two ranks, targets all-reduced, each rank steps its own CVNN replica
+    through the fused step: the replicas stay bit-identical and track the single-GPU run."""
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((queue.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, l0, a0, p0), (_, l1, a1, p1) = results
+    assert l0 == l1 and all(np.array_equal(x, y) for x, y in zip(p0, p1))
+    assert max(abs(x - y) / abs(y) for x, y in zip(l0, a0)) <= 1e-4  # sharded sums differ from single-GPU sums in the last bits only
