@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 python tools/ncu_summary.py gpurun_out/prof_fused_f32.ncu-rep gpurun_out/prof_fused_f64.ncu-rep gpurun_out/prof_materialised_terminal.ncu-rep gpurun_out/prof_materialised.ncu-rep > profiles/r1_ncu_summary.txt
-sed -i '1i # ncu --set full --clock-control none, one launch each (tools/prof_fused.py at config c2 sizes; float64 at B=8192).\n# prof_materialised.ncu-rep predates the generator rewrite (its philox_normals row is the old kernel; the in-place stepper is current).\n# The float64 capture predates the last float32-only codegen changes (the float64 kernel is unchanged since).\n' profiles/r1_ncu_summary.txt
+sed -i '1i # ncu --set full --clock-control none, one launch each (tools/prof_fused.py at config c2 sizes; float64 at B=8192), all captured from the final round-1 build.\n' profiles/r1_ncu_summary.txt
 ncu -i gpurun_out/prof_fused_f32.ncu-rep --page raw --csv 2>/dev/null > profiles/r1_fused_f32_ncu_raw.csv
 cp gpurun_out/launches_bench.csv profiles/r1_launches_bench.csv
 python tools/sass_loop.py _ZN3smc11tile_kernelIfLi0ELi0ELi0ELb0E --dump > profiles/r1_fused_f32_sass_inner_loop.txt 2>/dev/null
