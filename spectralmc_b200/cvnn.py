@@ -7,8 +7,10 @@ Two things live here:
   ``zReLU`` (:149-162), ``modReLU`` (:168-210, epsilon 1e-9 under the root) and
   ``ComplexSequential`` (:439-452) — same constructor arguments, parameter names and forward
   semantics, models mapping ``(real, imag) -> (real, imag)``.  Their ``forward`` is plain torch:
-  it is the generic route for networks the fused step does not cover (the batch norms and the
-  residual wrapper of the reference, cvnn.py:213-430,454-493, are not rebuilt).
+  it is the generic route for networks the fused step does not cover.  The remaining blocks the
+  reference's factory can emit — ``NaiveComplexBatchNorm`` (:213-274), ``CovarianceComplexBatchNorm``
+  (:277-433) and ``ComplexResidual`` (:454-493) — are provided with the same parameter / buffer
+  names (state dicts interchange with the reference's) and stay on the torch route.
 * ``FusedCVNN``: the same network driven through the C ABI (``smc_cvnn_forward``,
   ``smc_cvnn_train_step``): one complex GEMM per ``ComplexLinear`` with bias and activation in
   the epilogue, hand-derived backward, MSE loss and Adam (``GbmCVNNPricer._torch_step``,
@@ -87,6 +89,86 @@ class ComplexSequential(nn.Module):
 
     def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
         return reduce(lambda state, layer: layer(*state), self.layers, (real, imag))
+
+
+class NaiveComplexBatchNorm(nn.Module):
+    """``BatchNorm1d`` applied to the real and to the imaginary plane independently (reference
+    cvnn.py:213-274; sub-module names ``bn_real`` / ``bn_imag`` as there)."""
+
+    def __init__(self, num_features: int, *, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True,
+                 track_running_stats: bool = True) -> None:
+        super().__init__()
+        kw = dict(eps=eps, momentum=momentum, affine=affine, track_running_stats=track_running_stats)
+        self.bn_real = nn.BatchNorm1d(num_features, **kw)
+        self.bn_imag = nn.BatchNorm1d(num_features, **kw)
+
+    def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        return self.bn_real(real), self.bn_imag(imag)
+
+
+class CovarianceComplexBatchNorm(nn.Module):
+    """Whitening batch norm of Trabelsi et al. (reference cvnn.py:277-433): each feature's (re, im)
+    pair is centred and multiplied by ``V^{-1/2}`` of its 2x2 covariance ``V`` (+ eps on the
+    diagonal), then mapped by a learnable symmetric ``Gamma`` and shift ``beta``.
+
+    The reference forms ``V^{-1/2}`` with a batched ``eigh``; this class uses the closed form for a
+    symmetric positive-definite 2x2 matrix, ``V^{-1/2} = [[c + s, -b], [-b, a + s]] / (s t)`` with
+    ``s = sqrt(det V)``, ``t = sqrt(a + c + 2 s)`` — the same matrix (eigenvalues are >= eps, so the
+    reference's clamp never acts), without a LAPACK-style call per step.  Buffers and parameters keep
+    the reference's names, so state dicts interchange.
+    """
+
+    def __init__(self, num_features: int, *, eps: float = 1e-5, momentum: float = 0.1, affine: bool = True,
+                 track_running_stats: bool = True) -> None:
+        super().__init__()
+        self.eps, self.momentum, self.affine, self.track_running_stats = eps, momentum, affine, track_running_stats
+        for name, fill in (("running_mean_real", 0.0), ("running_mean_imag", 0.0), ("running_C_rr", 0.5), ("running_C_ri", 0.0),
+                           ("running_C_ii", 0.5)):
+            self.register_buffer(name, torch.full((num_features,), fill))
+        names = ("beta_real", "beta_imag", "gamma_rr", "gamma_ri", "gamma_ii")
+        init = (0.0, 0.0, 1.0, 0.0, 1.0)
+        for name, fill in zip(names, init):
+            if affine:
+                setattr(self, name, nn.Parameter(torch.full((num_features,), fill)))
+            else:
+                self.register_parameter(name, None)
+
+    def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        if self.training or not self.track_running_stats:
+            mu_r, mu_i = real.mean(dim=0), imag.mean(dim=0)
+            dr, di = real - mu_r, imag - mu_i
+            a, b, c = (dr * dr).mean(dim=0), (dr * di).mean(dim=0), (di * di).mean(dim=0)
+            if self.track_running_stats:
+                with torch.no_grad():
+                    for buf, val in ((self.running_mean_real, mu_r), (self.running_mean_imag, mu_i), (self.running_C_rr, a),
+                                     (self.running_C_ri, b), (self.running_C_ii, c)):
+                        buf.mul_(1 - self.momentum).add_(val * self.momentum)
+        else:
+            dr, di = real - self.running_mean_real, imag - self.running_mean_imag
+            a, b, c = self.running_C_rr, self.running_C_ri, self.running_C_ii
+        a, c = a + self.eps, c + self.eps
+        s = torch.sqrt(a * c - b * b)
+        inv = 1.0 / (s * torch.sqrt(a + c + 2.0 * s))
+        w_rr, w_ri, w_ii = (c + s) * inv, -b * inv, (a + s) * inv
+        white_r, white_i = w_rr * dr + w_ri * di, w_ri * dr + w_ii * di
+        if not self.affine:
+            return white_r, white_i
+        return (self.gamma_rr * white_r + self.gamma_ri * white_i + self.beta_real,
+                self.gamma_ri * white_r + self.gamma_ii * white_i + self.beta_imag)
+
+
+class ComplexResidual(nn.Module):
+    """``post_act(proj(x) + body(x))`` with optional projection and activation (reference cvnn.py:454-493)."""
+
+    def __init__(self, body: nn.Module, proj: nn.Module | None = None, post_act: nn.Module | None = None) -> None:
+        super().__init__()
+        self.body, self.proj, self.post_act = body, proj, post_act
+
+    def forward(self, real: torch.Tensor, imag: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        body_r, body_i = self.body(real, imag)
+        skip_r, skip_i = (real, imag) if self.proj is None else self.proj(real, imag)
+        out = (body_r + skip_r, body_i + skip_i)
+        return out if self.post_act is None else self.post_act(*out)
 
 
 def make_cvnn(n_inputs: int, n_outputs: int, *, hidden_width: int = 32, seed: int = 0,

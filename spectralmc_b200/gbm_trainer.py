@@ -138,7 +138,7 @@ class TrainingResult:
 
 
 def _module_device_dtype(module: nn.Module) -> Result[tuple[torch.device, torch.dtype], DeviceDTypeError]:
-    tensors = list(module.state_dict().values())
+    tensors = [t for t in module.state_dict().values() if t.is_floating_point()]  # BatchNorm keeps an int64 batch counter
     if not tensors:
         return Failure(DeviceDTypeError(message="CVNN has no parameters"))
     devices, dtypes = {t.device for t in tensors}, {t.dtype for t in tensors}

@@ -40,7 +40,7 @@ def pytest_collection_modifyitems(config: pytest.Config, items: list[pytest.Item
 
 
 def golden_cases() -> list[str]:
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "sobol_contracts.npz" and not f.startswith("cvnn_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz") and f != "sobol_contracts.npz" and not f.startswith("cvnn"))
 
 
 def load_golden(name: str) -> dict[str, np.ndarray]:

@@ -297,3 +297,33 @@ def test_wide_network_and_large_batch() -> None:
     assert abs(float(loss) - float(ref_loss.detach())) <= 1e-5 * float(ref_loss.detach())
     for p, g in zip(net.parameters(), ref_grads):
         assert nw(p.grad, g) <= 1e-4
+
+
+def test_factory_networks_with_batch_norm_and_residuals_train_on_the_torch_route() -> None:
+    """A network using every block of the reference's factory (batch norms, residuals) is outside the
+    fused step: the trainer takes the torch route for it, deterministically."""
+    from spectralmc_b200 import cvnn_factory as f
+
+    def act(kind):
+        return f.ActivationCfg(kind=kind)
+
+    def trainer():
+        layers = [
+            f.LinearCfg(width=f.ExplicitWidth(value=24), activation=act(f.ActivationKind.MOD_RELU)),
+            f.CovBNCfg(),
+            f.ResidualCfg(body=f.SequentialCfg(layers=[f.LinearCfg(activation=act(f.ActivationKind.Z_RELU)), f.NaiveBNCfg()]),
+                          activation=act(f.ActivationKind.MOD_RELU)),
+        ]
+        cfg = expect_success(f.build_cvnn_config(dtype=Precision.float32, layers=layers, seed=21))
+        net = expect_success(f.build_model(n_inputs=6, n_outputs=16, cfg=cfg)).to("cuda", torch.float32)
+        sp = make_simulation_params(timesteps=2, network_size=16, batches_per_mc_run=512, mc_seed=21, dtype=Precision.float32)
+        bs = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+        return expect_success(GbmCVNNPricer.create(expect_success(build_gbm_cvnn_pricer_config(cfg=bs, domain_bounds=make_domain_bounds(), cvnn=net))))
+
+    a, b = trainer(), trainer()
+    assert not a._use_fused
+    ra = expect_success(a.train(TrainingConfig(num_batches=3, batch_size=32)))
+    rb = expect_success(b.train(TrainingConfig(num_batches=3, batch_size=32)))
+    assert ra.losses == rb.losses and all(np.isfinite(ra.losses))
+    assert all(torch.equal(x, y) for x, y in zip(_params(a), _params(b)))
+    assert float(a._cvnn.state_dict()["layers.0.layers.1.running_C_rr"].sub(0.5).abs().max()) > 0  # statistics were tracked
