@@ -193,7 +193,9 @@ int smc_cf_from_terminal(const smc_fused_args* args, const void* terminal,
 /* Host-buffer convenience for the reference-facing call: copies `contracts_host`
  * (ideally pinned) to the device, runs smc_cf_fused, copies the [n_contracts, N] complex
  * result to `cf_host` and synchronises `stream`.  args->contracts is ignored.  The workspace
- * must be smc_cf_fused_host_workspace_bytes() (device memory). */
+ * must be smc_cf_fused_host_workspace_bytes() (device memory).  When a host buffer is pinned
+ * (cudaHostAlloc / cudaHostRegister) and at most 64 KiB, the kernels read / write it directly
+ * through its device alias instead of a staging copy; pageable buffers always take the copies. */
 size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* args);
 int smc_cf_fused_host(const smc_fused_args* args, const double* contracts_host, void* cf_host,
                       void* workspace, size_t workspace_bytes, void* stream);

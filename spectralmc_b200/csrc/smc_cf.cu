@@ -938,11 +938,30 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
   double* d_contracts = reinterpret_cast<double*>(base);
   void* d_out = base + align_up(cbytes);
   char* rest = base + align_up(cbytes) + align_up(obytes);
-  SMC_CUDA_OK(cudaMemcpyAsync(d_contracts, contracts_host, cbytes, cudaMemcpyHostToDevice, st));
+  // Pinned host buffers are device-addressable under unified addressing.  For small batches the
+  // two staging copies are pure latency (48 bytes in, 1 KiB out at config c2), so the contracts are
+  // read by the prep kernel, and the targets written by the finalise kernel, straight through the
+  // mapped pointers; pageable memory and large batches take the staged copies.
+  auto device_alias = [](const void* host) -> void* {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+      cudaGetLastError();  // unregistered pageable memory reports an error on older drivers: not sticky
+      return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+  };
+  constexpr size_t kZeroCopyMax = 64 << 10;
+  void* c_alias = cbytes <= kZeroCopyMax ? device_alias(contracts_host) : nullptr;
+  void* o_alias = obytes <= kZeroCopyMax ? device_alias(cf_host) : nullptr;
   smc_fused_args b = *a;
-  b.contracts = d_contracts;
-  if (int e = smc_cf_fused(&b, d_out, rest, ws_bytes - align_up(cbytes) - align_up(obytes), stream)) return e;
-  SMC_CUDA_OK(cudaMemcpyAsync(cf_host, d_out, obytes, cudaMemcpyDeviceToHost, st));
+  if (c_alias) {
+    b.contracts = static_cast<const double*>(c_alias);
+  } else {
+    SMC_CUDA_OK(cudaMemcpyAsync(d_contracts, contracts_host, cbytes, cudaMemcpyHostToDevice, st));
+    b.contracts = d_contracts;
+  }
+  if (int e = smc_cf_fused(&b, o_alias ? o_alias : d_out, rest, ws_bytes - align_up(cbytes) - align_up(obytes), stream)) return e;
+  if (!o_alias) SMC_CUDA_OK(cudaMemcpyAsync(cf_host, d_out, obytes, cudaMemcpyDeviceToHost, st));
   SMC_CUDA_OK(cudaStreamSynchronize(st));
   return SMC_OK;
 }

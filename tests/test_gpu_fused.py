@@ -136,13 +136,31 @@ def test_bit_reproducible_and_skip_semantics() -> None:
     assert not np.array_equal(a[0], a[2])  # same contract, different matrix
 
 
-def test_host_buffer_entry_point() -> None:
-    rows = torch.tensor([CANON, ODD], dtype=torch.float64).pin_memory()
+@pytest.mark.parametrize("pin_in,pin_out", [(True, True), (False, False), (True, False), (False, True)])
+def test_host_buffer_entry_point(pin_in, pin_out) -> None:
+    """Pinned buffers are read / written through their device alias (no staging copy), pageable ones
+    through the staged copies; every combination gives the device-resident result bit for bit."""
+    rows = torch.tensor([CANON, ODD], dtype=torch.float64)
+    out = torch.full((2, 16), float("nan"), dtype=torch.complex64)
+    rows = rows.pin_memory() if pin_in else rows
+    out = out.pin_memory() if pin_out else out
     args = _cabi.make_fused_args(None, 2, 12, 16, 64, torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 42, 0)
-    out = torch.empty((2, 16), dtype=torch.complex64).pin_memory()
     ws = torch.empty(_cabi.cf_fused_host_workspace_bytes(args), dtype=torch.uint8, device="cuda")
     _cabi.cf_fused_host(args, rows, out, ws)
     dev = _fused([CANON, ODD], 12, 16, 64, torch.float32, 42, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    assert np.array_equal(out.numpy(), dev)
+
+
+def test_host_buffer_entry_point_large_batch_takes_the_staged_copies() -> None:
+    """Above 64 KiB the pinned buffers go through cudaMemcpyAsync (DMA beats kernel stores over PCIe)."""
+    C, N = 600, 32  # 600 * 32 * 8 B = 150 KiB of targets
+    rows_np = sobol_contracts(C, seed=9)
+    rows = torch.tensor(rows_np, dtype=torch.float64).pin_memory()
+    out = torch.full((C, N), float("nan"), dtype=torch.complex64).pin_memory()
+    args = _cabi.make_fused_args(None, C, 3, N, 8, torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 42, 0)
+    ws = torch.empty(_cabi.cf_fused_host_workspace_bytes(args), dtype=torch.uint8, device="cuda")
+    _cabi.cf_fused_host(args, rows, out, ws)
+    dev = _fused(rows_np, 3, N, 8, torch.float32, 42, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
     assert np.array_equal(out.numpy(), dev)
 
 
