@@ -380,6 +380,22 @@ __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real)
   }
 }
 
+// s += v[0] + v[stride] + ... (count terms), in index order, with eight loads in flight: these
+// second-level reductions read L2-resident partials and are bound by load latency, not bandwidth.
+__device__ __forceinline__ double strided_sum(const double* __restrict__ v, int64_t count, int64_t stride) {
+  double s = 0.0;
+  int64_t i = 0;
+  for (; i + 8 <= count; i += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = v[(i + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u];
+  }
+  for (; i < count; ++i) s += v[i * stride];
+  return s;
+}
+
 // level 1: groups of tile partials -> [contracts, groups, n].  When n <= 128 the CTA's 256 threads
 // split into `subs` lanes per column, each summing every subs-th tile of the group; the lanes are
 // folded in shared memory in a fixed order.
@@ -392,17 +408,8 @@ __global__ void __launch_bounds__(CF_BLOCK)
   const double* src = partial + c * tiles * n;
   if (subs > 1) {  // n * subs == CF_BLOCK
     const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
-    double s = 0.0;
-    int64_t t = t0 + sub;
-    for (; t + 3 * subs < t1; t += 4 * subs) {
-      const double a = src[t * n + col], b = src[(t + subs) * n + col];
-      const double cc = src[(t + 2 * subs) * n + col], d = src[(t + 3 * subs) * n + col];
-      s += a;
-      s += b;
-      s += cc;
-      s += d;
-    }
-    for (; t < t1; t += subs) s += src[t * n + col];
+    const int64_t mine = t0 + sub < t1 ? (t1 - t0 - sub + subs - 1) / subs : 0;  // tiles t0 + sub, t0 + sub + subs, ...
+    const double s = strided_sum(src + (t0 + sub) * n + col, mine, static_cast<int64_t>(subs) * n);
     sm[threadIdx.x] = s;
     __syncthreads();
     if (sub == 0) {
@@ -412,20 +419,8 @@ __global__ void __launch_bounds__(CF_BLOCK)
     }
     return;
   }
-  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
-    double s = 0.0;
-    int64_t t = t0;
-    for (; t + 4 <= t1; t += 4) {
-      const double a = src[(t + 0) * n + col], b = src[(t + 1) * n + col];
-      const double cc = src[(t + 2) * n + col], d = src[(t + 3) * n + col];
-      s += a;
-      s += b;
-      s += cc;
-      s += d;
-    }
-    for (; t < t1; ++t) s += src[t * n + col];
-    grouped[(c * groups + g) * n + col] = s;
-  }
+  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK)
+    grouped[(c * groups + g) * n + col] = strided_sum(src + t0 * n + col, t1 - t0, n);
 }
 
 // sum of a contract's per-tile terminal sums (fixed order)
@@ -493,8 +488,7 @@ __global__ void __launch_bounds__(CF_BLOCK)
     twi[j] = sn;
   }
   for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
-    double s = 0.0;
-    for (int64_t g = 0; g < groups; ++g) s += src[g * n + col];
+    const double s = strided_sum(src + col, groups, n);
     int64_t where = col;
     if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
     re[where] = s * scale;
