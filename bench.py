@@ -160,7 +160,7 @@ def workload_config(name: str, gpus: int) -> dict:
     return {
         "workload": f"{name}: {w['contracts']} contract(s) {w['dtype']}, T={w['T']}, N={w['N']}, B={w['B']} per GPU, RAW, LOG_EULER, fused Philox normals",
         "contracts_per_step": w["contracts"], "timesteps": w["T"], "network_size": w["N"],
-        "batches_per_gpu": w["B"], "batches_total": w["B"] * gpus, "parallelism": f"batch-shard x{gpus} + 1 allreduce" if gpus > 1 else "single GPU",
+        "batches_per_gpu": w["B"], "batches_total": w["B"] * gpus, "parallelism": f"batch-shard x{gpus}, one exchange of the partial sums per step" if gpus > 1 else "single GPU",
         "l2": "fused mode has no HBM-resident inputs (normals are drawn in registers); a 256 MiB L2 flush runs between timed steps anyway; materialised-mode inputs (8.5 GB) exceed L2",
     }
 
@@ -201,13 +201,40 @@ def run_b200(args) -> None:
                                      batch_begin=rank * B, batch_end=(rank + 1) * B)
 
     ws = torch.empty(_cabi.cf_fused_host_workspace_bytes(make_args(0, None)) + 4096, dtype=torch.uint8, device=dev)
+    # multi-GPU exchange of the partial sums: fused into the finalise kernel over peer memory
+    # (smc_cf_fused_p2p) when the IPC set-up succeeds, else one ncclAllReduce after the kernels
+    exchange, collective = None, "none"
+    if world > 1:
+        collective = "nccl allreduce"
+        if args.collective in ("auto", "p2p"):
+            try:
+                from spectralmc_b200.distributed import PeerExchange
+
+                exchange = PeerExchange(C, N)
+                collective = "fused peer-memory exchange (smc_cf_fused_p2p)"
+            except Exception as exc:  # noqa: BLE001 - any set-up failure falls back to the NCCL route, visibly
+                if args.collective == "p2p":
+                    raise
+                collective = f"nccl allreduce (peer exchange unavailable: {type(exc).__name__}: {exc})"
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank must take the same route
+        if int(ok.item()) == 0 and exchange is not None:
+            exchange, collective = None, "nccl allreduce (peer exchange unavailable on another rank)"
+
+    def sharded(step: int, contracts):
+        a = make_args(step, contracts)
+        if exchange is not None:
+            return _cabi.cf_fused_p2p(a, exchange.next_group(), dev, dtype, ws)
+        out = _cabi.cf_fused(a, dev, dtype, ws)
+        if world > 1:
+            dist.all_reduce(torch.view_as_real(out))
+        return out
+
     launches = {"n": 0}
     plan_launches = int(_cabi.LIB.smc_cf_fused_launch_count(_cabi.byref(make_args(0, None))))
 
     def step_device(step: int):
-        out = _cabi.cf_fused(make_args(step, contracts_dev), dev, dtype, ws)
-        if world > 1:
-            dist.all_reduce(torch.view_as_real(out))
+        out = sharded(step, contracts_dev)
         launches["n"] += plan_launches
         return out
 
@@ -216,8 +243,7 @@ def run_b200(args) -> None:
             _cabi.cf_fused_host(make_args(step, None), contracts_pin, out_pin, ws)  # H2D + kernels + D2H + sync
         else:
             cdev = contracts_pin.to(dev, non_blocking=True)
-            out = _cabi.cf_fused(make_args(step, cdev), dev, dtype, ws)
-            dist.all_reduce(torch.view_as_real(out))
+            out = sharded(step, cdev)
             out_pin.copy_(out, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         launches["n"] += plan_launches
@@ -265,11 +291,11 @@ def run_b200(args) -> None:
         "metric": "gbm_path_steps_per_sec", "value": value, "unit": "path-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32" if dtype == torch.float32 else "f64", "data": "synthetic",
-        "config": workload_config(args.workload, world),
+        "config": dict(workload_config(args.workload, world), collective=collective),
         "cf_estimates_per_sec": C * args.steps / (ms_dev * 1e-3),
         "e2e": {"value": e2e_value, "unit": "path-steps/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(contracts_pin.numel() * 8), "d2h_bytes_per_step": int(out_pin.numel() * out_pin.element_size()),
-                "api": "smc_cf_fused_host (C ABI, pinned host buffers)" if world == 1 else "H2D + smc_cf_fused + ncclAllReduce + D2H"},
+                "api": "smc_cf_fused_host (C ABI, pinned host buffers)" if world == 1 else f"H2D + sharded fused path [{collective}] + D2H"},
         "gpu_launches": launches["n"], "clocks": clk,
     }
 
@@ -306,6 +332,8 @@ def run_b200(args) -> None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        if exchange is not None:
+            exchange.close()
         dist.destroy_process_group()
 
 
@@ -363,6 +391,8 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--collective", default="auto", choices=("auto", "p2p", "nccl"),
+                    help="multi-GPU exchange: fused peer-memory exchange, NCCL all-reduce, or the former with fallback to the latter")
     ap.add_argument("--cpu-sample-batches", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

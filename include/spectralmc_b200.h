@@ -190,6 +190,39 @@ int smc_cf_from_terminal(const smc_fused_args* args, const void* terminal,
                          const double* terminal_sum_global /* device double[C] or NULL */,
                          void* cf_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Batch-sharded RAW runs with the all-reduce FUSED into the finalise kernel over peer memory
+ * (NVLink / NVSwitch) — the multi-GPU form of smc_cf_fused: same arguments and sharding
+ * contract, but cf_out receives the COMPLETE [n_contracts, N] targets on every rank, with no
+ * separate collective: each rank stores its float64 partial column sums straight into every
+ * peer's exchange buffer, publishes a per-contract flag, waits for the peers' flags, sums the
+ * `world` vectors in rank order (identical bits on every rank) and takes the one transform.
+ *
+ * Exchange buffers: one per rank, allocated by smc_p2p_alloc (cudaMalloc, zeroed, exported as a
+ * 64-byte cudaIpc handle), opened by the other ranks with smc_p2p_open; all ranks must have
+ * finished allocating and opening before the first call (a barrier of the caller's process group).
+ * `epoch` must be > 0, equal on all ranks for one call and strictly increasing from call to call;
+ * all ranks must make the same sequence of calls on one stream each.  A peer that never arrives
+ * makes the kernel trap after ~2^28 polls (CUDA error at the next synchronisation, no hang).
+ */
+typedef struct smc_p2p_group {
+  int rank;
+  int world;                   /* <= 16 */
+  void* buffers[16];           /* buffers[q]: rank q's exchange buffer as mapped in THIS process */
+  int64_t capacity_contracts;  /* what the buffers were sized for (smc_p2p_buffer_bytes)        */
+  int64_t network_size;
+  uint32_t epoch;
+} smc_p2p_group;
+
+size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world);
+int smc_p2p_alloc(size_t bytes, void** ptr, void* handle64 /* out: 64 bytes */);
+int smc_p2p_open(const void* handle64, void** ptr);
+int smc_p2p_close(void* ptr);
+int smc_p2p_free(void* ptr);
+int smc_cf_fused_p2p(const smc_fused_args* args, const smc_p2p_group* group, void* cf_out,
+                     void* workspace /* smc_cf_fused_workspace_bytes(args) */, size_t workspace_bytes,
+                     void* stream);
+
 /* Host-buffer convenience for the reference-facing call: copies `contracts_host`
  * (ideally pinned) to the device, runs smc_cf_fused, copies the [n_contracts, N] complex
  * result to `cf_host` and synchronises `stream`.  args->contracts is ignored.  The workspace

@@ -33,7 +33,8 @@ EXPORTS = (
     "smc_cf_from_terminal_workspace_bytes smc_cf_from_terminal smc_cf_fused_host_workspace_bytes "
     "smc_cf_fused_host smc_pipe_calibrate "
     "smc_cvnn_workspace_bytes smc_cvnn_output_width smc_cvnn_forward smc_cvnn_loss_backward smc_adam_step "
-    "smc_cvnn_train_step"
+    "smc_cvnn_train_step "
+    "smc_p2p_buffer_bytes smc_p2p_alloc smc_p2p_open smc_p2p_close smc_p2p_free smc_cf_fused_p2p"
 ).split()
 
 SMC_LAYER_LINEAR, SMC_LAYER_MODRELU, SMC_LAYER_ZRELU = 0, 1, 2
@@ -64,6 +65,19 @@ class FusedArgs(Structure):
         ("normalization", c_int),
         ("seed", c_uint64),
         ("first_matrix_index", c_uint64),
+    ]
+
+
+class P2PGroup(Structure):
+    """``smc_p2p_group`` (include/spectralmc_b200.h)."""
+
+    _fields_ = [
+        ("rank", c_int),
+        ("world", c_int),
+        ("buffers", c_void_p * 16),
+        ("capacity_contracts", c_int64),
+        ("network_size", c_int64),
+        ("epoch", ctypes.c_uint32),
     ]
 
 
@@ -138,6 +152,13 @@ def _load() -> ctypes.CDLL:
     lib.smc_cf_from_terminal.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cf_fused_host.argtypes = [POINTER(FusedArgs), c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_pipe_calibrate.argtypes = [c_int, c_int64, POINTER(c_double), c_void_p, c_void_p]
+    lib.smc_p2p_buffer_bytes.argtypes = [c_int64, c_int64, c_int]
+    lib.smc_p2p_buffer_bytes.restype = c_size_t
+    lib.smc_p2p_alloc.argtypes = [c_size_t, POINTER(c_void_p), c_void_p]
+    lib.smc_p2p_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    lib.smc_p2p_close.argtypes = [c_void_p]
+    lib.smc_p2p_free.argtypes = [c_void_p]
+    lib.smc_cf_fused_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cvnn_workspace_bytes.argtypes = [POINTER(CvnnNet), c_int64, c_int]
     lib.smc_cvnn_output_width.argtypes = [POINTER(CvnnNet)]
     lib.smc_cvnn_output_width.restype = c_int64
@@ -477,3 +498,28 @@ def cvnn_train_step(net: CvnnNet, params: torch.Tensor, grads: torch.Tensor, exp
             workspace.data_ptr(), workspace.numel(), _stream(),
         )
     )
+
+
+# --------------------------------------------------------------------------- peer-memory exchange
+def p2p_alloc(nbytes: int) -> tuple[int, bytes]:
+    """Allocate a zeroed exchange buffer on the current device; returns (device pointer, 64-byte IPC handle)."""
+    ptr = c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    check(LIB.smc_p2p_alloc(nbytes, byref(ptr), handle))
+    return int(ptr.value), handle.raw
+
+
+def p2p_open(handle: bytes) -> int:
+    ptr = c_void_p()
+    check(LIB.smc_p2p_open(ctypes.create_string_buffer(handle, 64), byref(ptr)))
+    return int(ptr.value)
+
+
+def cf_fused_p2p(args: FusedArgs, group: P2PGroup, device: torch.device, dtype: torch.dtype,
+                 workspace: torch.Tensor | None = None) -> torch.Tensor:
+    """Sharded fused batch path with the all-reduce fused into the finalise kernel: COMPLETE targets on every rank."""
+    out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=device)
+    need = LIB.smc_cf_fused_workspace_bytes(byref(args))
+    ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, device)
+    check(LIB.smc_cf_fused_p2p(byref(args), byref(group), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out

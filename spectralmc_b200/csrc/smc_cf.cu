@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 
 #include "smc_device.cuh"
 #include "smc_internal.h"
@@ -436,66 +437,23 @@ __global__ void __launch_bounds__(CF_BLOCK)
 
 __device__ __forceinline__ unsigned bit_reverse(unsigned x, int bits) { return __brev(x) >> (32 - bits); }
 
-// One CTA per contract: fold `groups` vectors, scale, transform, narrow.
-// Shared memory (doubles): re[n], im[n], then the twiddle table (n/2 pairs for radix-2, n pairs for
-// the DFT).  mode: 0 radix-2 (n power of two), 1 table DFT, 2 DFT with on-the-fly twiddles and the
-// folded vector staged in `spill` (global) for n too large for shared memory.
-template <typename Real>
-__global__ void __launch_bounds__(CF_BLOCK)
-    cf_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
-                       int log2n, Real* __restrict__ out /* [contracts, n, 2] */, int64_t out_contract0,
-                       double* __restrict__ spill) {
-  extern __shared__ double smem[];
-  const int64_t c = blockIdx.x;
-  const double* src = vecs + c * groups * n;
-  Real* dst = out + (out_contract0 + c) * n * 2;
+// exp(-2 pi i j / n) for j < ntw into (twr, twi)
+__device__ __forceinline__ void fill_twiddles(double* twr, double* twi, int64_t ntw, int64_t n) {
   const double kTwoOverN = 2.0 / static_cast<double>(n);
-
-  if (mode == 2) {
-    double* x = spill + c * n;
-    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
-      double s = 0.0;
-      for (int64_t g = 0; g < groups; ++g) s += src[g * n + col];
-      x[col] = s * scale;
-    }
-    __syncthreads();  // x is written and read by this CTA only
-    for (int64_t kk = threadIdx.x; kk < n; kk += CF_BLOCK) {
-      double re = 0.0, im = 0.0;
-      int64_t m = 0;
-      for (int64_t j = 0; j < n; ++j) {
-        double sn, cs;
-        sincospi(-static_cast<double>(m) * kTwoOverN, &sn, &cs);
-        re = fma(x[j], cs, re);
-        im = fma(x[j], sn, im);
-        m += kk;
-        if (m >= n) m -= n;
-      }
-      dst[2 * kk] = static_cast<Real>(re);
-      dst[2 * kk + 1] = static_cast<Real>(im);
-    }
-    return;
-  }
-
-  double* re = smem;
-  double* im = smem + n;
-  double* twr = smem + 2 * n;
-  double* twi = twr + (mode == 0 ? n / 2 : n);
-  const int64_t ntw = mode == 0 ? n / 2 : n;
   for (int64_t j = threadIdx.x; j < ntw; j += CF_BLOCK) {
     double sn, cs;
-    sincospi(-static_cast<double>(j) * kTwoOverN, &sn, &cs);  // exp(-2 pi i j / n)
+    sincospi(-static_cast<double>(j) * kTwoOverN, &sn, &cs);
     twr[j] = cs;
     twi[j] = sn;
   }
-  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
-    const double s = strided_sum(src + col, groups, n);
-    int64_t where = col;
-    if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
-    re[where] = s * scale;
-    im[where] = 0.0;
-  }
-  __syncthreads();
+}
 
+// Length-n forward transform of the real vector in shared memory and narrowing store.  mode 0: `re`
+// holds the input in bit-reversed order, `im` zeros (radix-2, in place); mode 1: `re` holds the input
+// in natural order (table-driven DFT).  All threads of the CTA; the input must be visible (synced).
+template <typename Real>
+__device__ __forceinline__ void transform_store(double* re, double* im, const double* twr, const double* twi,
+                                                int64_t n, int mode, Real* __restrict__ dst) {
   if (mode == 0) {
     for (int64_t half = 1; half < n; half <<= 1) {
       const int64_t stride = n / (2 * half);
@@ -529,6 +487,148 @@ __global__ void __launch_bounds__(CF_BLOCK)
       dst[2 * kk] = static_cast<Real>(ar);
       dst[2 * kk + 1] = static_cast<Real>(ai);
     }
+  }
+}
+
+// One CTA per contract: fold `groups` vectors, scale, transform, narrow.
+// Shared memory (doubles): re[n], im[n], then the twiddle table (n/2 pairs for radix-2, n pairs for
+// the DFT).  mode: 0 radix-2 (n power of two), 1 table DFT, 2 DFT with on-the-fly twiddles and the
+// folded vector staged in `spill` (global) for n too large for shared memory.
+template <typename Real>
+__global__ void __launch_bounds__(CF_BLOCK)
+    cf_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
+                       int log2n, Real* __restrict__ out /* [contracts, n, 2] */, int64_t out_contract0,
+                       double* __restrict__ spill) {
+  extern __shared__ double smem[];
+  const int64_t c = blockIdx.x;
+  const double* src = vecs + c * groups * n;
+  Real* dst = out + (out_contract0 + c) * n * 2;
+
+  if (mode == 2) {
+    const double kTwoOverN = 2.0 / static_cast<double>(n);
+    double* x = spill + c * n;
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) x[col] = strided_sum(src + col, groups, n) * scale;
+    __syncthreads();  // x is written and read by this CTA only
+    for (int64_t kk = threadIdx.x; kk < n; kk += CF_BLOCK) {
+      double re = 0.0, im = 0.0;
+      int64_t m = 0;
+      for (int64_t j = 0; j < n; ++j) {
+        double sn, cs;
+        sincospi(-static_cast<double>(m) * kTwoOverN, &sn, &cs);
+        re = fma(x[j], cs, re);
+        im = fma(x[j], sn, im);
+        m += kk;
+        if (m >= n) m -= n;
+      }
+      dst[2 * kk] = static_cast<Real>(re);
+      dst[2 * kk + 1] = static_cast<Real>(im);
+    }
+    return;
+  }
+
+  double* re = smem;
+  double* im = smem + n;
+  double* twr = smem + 2 * n;
+  double* twi = twr + (mode == 0 ? n / 2 : n);
+  fill_twiddles(twr, twi, mode == 0 ? n / 2 : n, n);
+  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+    const double s = strided_sum(src + col, groups, n);
+    int64_t where = col;
+    if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
+    re[where] = s * scale;
+    im[where] = 0.0;
+  }
+  __syncthreads();
+  transform_store<Real>(re, im, twr, twi, n, mode, dst);
+}
+
+// ---- fused finalise + all-reduce over peer memory (NVLink / NVSwitch) ---------------------------
+// Multi-GPU form of cf_finalize_kernel for batch-sharded RAW runs: instead of transforming its local
+// partial sums and handing the complex result to ncclAllReduce, every rank
+//   phase 1  folds its groups into the real length-n vector x_rank (float64, already scaled by
+//            1 / B_total) and STORES it into a slot of every peer's exchange buffer (its own
+//            included), then publishes a per-contract flag on each peer (release, system scope);
+//   phase 2  waits for the flags of all ranks on its own buffer (acquire), sums the `world` vectors in
+//            rank order — every rank forms the identical float64 sum — and takes the ONE transform.
+// The exchange therefore moves n doubles per contract and rank (half of what the complex all-reduce
+// moves), carries the sum in float64, and costs one launch with no host involvement.
+// Deadlock freedom: the grid is persistent and never larger than the number of co-resident CTAs;
+// every CTA finishes phase 1 (which never waits) for all of its contracts before it waits in phase 2,
+// so every flag a peer waits for is written by a CTA that is already running.  Slots alternate with the
+// epoch parity: a rank can be at most one call ahead of a peer, because its phase 2 of call k needs
+// that peer's phase 1 of call k.  A wait that exceeds ~2^28 polls traps (diagnosable error, no hang).
+constexpr int MAX_PEERS = 16;
+
+struct PeerExchange {
+  double* data[MAX_PEERS];     // exchange buffer of rank p as mapped into this process
+  int rank, world;
+  unsigned epoch;              // > 0, the same on every rank for one call, increasing
+  int64_t capacity_contracts;  // contracts the buffers were sized for
+};
+
+__host__ __device__ inline size_t exchange_data_doubles(int64_t capacity_contracts, int64_t n, int world) {
+  return static_cast<size_t>(2) * world * capacity_contracts * n;
+}
+
+__device__ __forceinline__ void store_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned load_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <typename Real>
+__global__ void __launch_bounds__(CF_BLOCK)
+    cf_exchange_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
+                                int log2n, Real* __restrict__ out, int64_t contracts, const PeerExchange px) {
+  extern __shared__ double smem[];
+  double* re = smem;
+  double* im = smem + n;
+  double* twr = smem + 2 * n;
+  double* twi = twr + (mode == 0 ? n / 2 : n);
+  fill_twiddles(twr, twi, mode == 0 ? n / 2 : n, n);
+
+  const int64_t cap = px.capacity_contracts;
+  const int64_t slot = px.epoch & 1u;
+  const size_t flag_base = exchange_data_doubles(cap, n, px.world);  // flags follow the data (as 8-byte cells)
+
+  // phase 1: fold, push to every peer, publish
+  for (int64_t c = blockIdx.x; c < contracts; c += gridDim.x) {
+    const double* src = vecs + c * groups * n;
+    const size_t cell = ((slot * px.world + px.rank) * cap + c);
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      const double x = strided_sum(src + col, groups, n) * scale;
+      for (int p = 0; p < px.world; ++p) px.data[p][cell * n + col] = x;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < px.world)
+      store_release_sys(reinterpret_cast<unsigned*>(px.data[threadIdx.x] + flag_base + cell), px.epoch);
+  }
+
+  // phase 2: wait for every rank's vector of this contract, sum in rank order, transform
+  const double* mine = px.data[px.rank];
+  for (int64_t c = blockIdx.x; c < contracts; c += gridDim.x) {
+    if (threadIdx.x < px.world) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(mine + flag_base + ((slot * px.world + threadIdx.x) * cap + c));
+      unsigned polls = 0;
+      while (load_acquire_sys(flag) != px.epoch)
+        if (++polls > (1u << 28)) __trap();
+    }
+    __syncthreads();
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      double s = 0.0;
+      for (int q = 0; q < px.world; ++q) s += __ldcv(mine + ((slot * px.world + q) * cap + c) * n + col);
+      int64_t where = col;
+      if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
+      re[where] = s;
+      im[where] = 0.0;
+    }
+    __syncthreads();
+    transform_store<Real>(re, im, twr, twi, n, mode, out + c * n * 2);
+    __syncthreads();  // re / im are reused by the next contract of this CTA
   }
 }
 
@@ -782,6 +882,110 @@ extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, siz
   SMC_REQUIRE(ws != nullptr, "smc_cf_fused: workspace is NULL");
   return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, cf_out, ws, ws_bytes, as_stream(stream))
                              : cf_fused_impl<double>(a, cf_out, ws, ws_bytes, as_stream(stream));
+}
+
+// ---- batch-sharded RAW with the all-reduce fused into the finalise kernel (peer memory) ------------
+extern "C" size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world) {
+  if (capacity_contracts <= 0 || network_size <= 0 || world <= 0 || world > MAX_PEERS) return 0;
+  return (exchange_data_doubles(capacity_contracts, network_size, world) +
+          static_cast<size_t>(2) * world * capacity_contracts) * sizeof(double);
+}
+
+extern "C" int smc_p2p_alloc(size_t bytes, void** ptr, void* handle64) {
+  clear_error();
+  SMC_REQUIRE(bytes > 0 && ptr && handle64, "smc_p2p_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  SMC_CUDA_OK(cudaMalloc(ptr, bytes));
+  SMC_CUDA_OK(cudaMemset(*ptr, 0, bytes));  // epochs start at 1: a zeroed flag is "not yet"
+  SMC_CUDA_OK(cudaDeviceSynchronize());
+  SMC_CUDA_OK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
+  return SMC_OK;
+}
+
+extern "C" int smc_p2p_open(const void* handle64, void** ptr) {
+  clear_error();
+  SMC_REQUIRE(handle64 && ptr, "smc_p2p_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  SMC_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return SMC_OK;
+}
+
+extern "C" int smc_p2p_close(void* ptr) {
+  clear_error();
+  SMC_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return SMC_OK;
+}
+
+extern "C" int smc_p2p_free(void* ptr) {
+  clear_error();
+  SMC_CUDA_OK(cudaFree(ptr));
+  return SMC_OK;
+}
+
+template <typename Real>
+static int cf_fused_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
+                             cudaStream_t st) {
+  const int64_t rows = a->batch_end - a->batch_begin;
+  const int64_t n = a->network_size;
+  const TilePlan plan = make_plan(a->n_contracts, rows, n);
+  const FinalizePlan f = finalize_plan(n);
+  if (f.mode == 2) return set_error(SMC_EUNSUPPORTED, "smc_cf_fused_p2p: network_size %lld needs the spill transform", (long long)n);
+  if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
+    return set_error(SMC_EWORKSPACE, "smc_cf_fused_p2p: workspace %zu < %zu", ws_bytes, colsum_bytes(plan, a->n_contracts, n));
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
+  TileParams p = base_params(a, plan);
+  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
+  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
+  if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
+  const double* vecs = p.partial;
+  int64_t groups = plan.tiles;
+  if (plan.tiles > MAX_GROUPS) {
+    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
+    reduce_tiles_kernel<<<static_cast<unsigned>(plan.groups * a->n_contracts), CF_BLOCK, 0, st>>>(
+        p.partial, grouped, plan.tiles, plan.tiles_per_group, plan.groups, n, subs);
+    SMC_LAUNCH_OK("reduce_tiles_kernel");
+    vecs = grouped;
+    groups = plan.groups;
+  }
+  if (f.smem > 48 * 1024)
+    SMC_CUDA_OK(cudaFuncSetAttribute(cf_exchange_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(f.smem)));
+  int per_sm = 0;
+  SMC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf_exchange_finalize_kernel<Real>, CF_BLOCK, f.smem));
+  const int64_t resident = static_cast<int64_t>(per_sm) * sm_count();
+  SMC_REQUIRE(resident > 0, "smc_cf_fused_p2p: the exchange kernel does not fit on an SM");
+  PeerExchange px{};
+  for (int q = 0; q < g->world; ++q) px.data[q] = static_cast<double*>(g->buffers[q]);
+  px.rank = g->rank;
+  px.world = g->world;
+  px.epoch = g->epoch;
+  px.capacity_contracts = g->capacity_contracts;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(a->n_contracts, resident));  // co-resident: see the kernel
+  cf_exchange_finalize_kernel<Real><<<grid, CF_BLOCK, f.smem, st>>>(
+      vecs, groups, n, 1.0 / static_cast<double>(a->batches_total), f.mode, f.log2n, static_cast<Real*>(cf_out),
+      a->n_contracts, px);
+  SMC_LAUNCH_OK("cf_exchange_finalize_kernel");
+  return SMC_OK;
+}
+
+extern "C" int smc_cf_fused_p2p(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  clear_error();
+  if (int e = check_args("smc_cf_fused_p2p", a)) return e;
+  SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr && ws != nullptr && g != nullptr, "smc_cf_fused_p2p: NULL pointer");
+  SMC_REQUIRE(a->normalization == SMC_RAW,
+              "smc_cf_fused_p2p: NORMALIZE needs the global terminal mean first (smc_fused_terminal + allreduce + smc_cf_from_terminal)");
+  SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world, "smc_cf_fused_p2p: bad rank %d of %d",
+              g->rank, g->world);
+  SMC_REQUIRE(g->epoch > 0, "smc_cf_fused_p2p: epoch must be > 0 (zero marks an unwritten flag)");
+  SMC_REQUIRE(a->n_contracts <= g->capacity_contracts && a->network_size == g->network_size,
+              "smc_cf_fused_p2p: exchange buffers sized for %lld contracts x %lld, call has %lld x %lld",
+              (long long)g->capacity_contracts, (long long)g->network_size, (long long)a->n_contracts, (long long)a->network_size);
+  for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "smc_cf_fused_p2p: buffer of rank %d is NULL", q);
+  return a->dtype == SMC_F32 ? cf_fused_p2p_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
+                             : cf_fused_p2p_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
 }
 
 // ---- two-phase API for batch-sharded NORMALIZE -------------------------------------------

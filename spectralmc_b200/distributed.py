@@ -71,6 +71,53 @@ class _CabiOps:
         return _cabi.cf_from_terminal(args, terminal, tsum, self.dtype)
 
 
+class PeerExchange:
+    """Exchange buffers for the peer-memory all-reduce fused into the finalise kernel
+    (``smc_cf_fused_p2p``): one cudaMalloc'ed buffer per rank, exported over cudaIpc and mapped by
+    every other rank of ``group`` (all ranks on one node, NVLink / NVSwitch peers).
+
+    ``torch.distributed`` is used once, to swap the 64-byte handles and to fence the set-up; the data
+    path afterwards has no collective call.  Every rank must call ``sharded_cf_targets(..., exchange=)``
+    the same number of times (the epoch counter advances in lock-step).
+    """
+
+    def __init__(self, capacity_contracts: int, network_size: int, *, group=None) -> None:
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("the peer exchange supports at most 16 ranks")
+        self.capacity_contracts, self.network_size = capacity_contracts, network_size
+        nbytes = int(_cabi.LIB.smc_p2p_buffer_bytes(capacity_contracts, network_size, self.world))
+        self._own, handle = _cabi.p2p_alloc(nbytes)
+        handles: list[bytes | None] = [None] * self.world
+        dist.all_gather_object(handles, handle, group=group)
+        self._peers = [self._own if q == self.rank else _cabi.p2p_open(handles[q]) for q in range(self.world)]
+        self.epoch = 0
+        dist.barrier(group=group)  # every buffer is zeroed and mapped before anyone writes
+
+    def next_group(self) -> "_cabi.P2PGroup":
+        self.epoch += 1
+        g = _cabi.P2PGroup()
+        g.rank, g.world = self.rank, self.world
+        for q, ptr in enumerate(self._peers):
+            g.buffers[q] = ptr
+        g.capacity_contracts, g.network_size, g.epoch = self.capacity_contracts, self.network_size, self.epoch
+        return g
+
+    def close(self) -> None:
+        if self._peers:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody is still writing into a buffer that is about to go away
+            for q, ptr in enumerate(self._peers):
+                if q != self.rank:
+                    _cabi.check(_cabi.LIB.smc_p2p_close(ptr))
+            dist.barrier(group=self.group)
+            _cabi.check(_cabi.LIB.smc_p2p_free(self._own))
+            self._peers = []
+
+
 def _all_reduce_sum(t: torch.Tensor, group) -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
@@ -83,6 +130,7 @@ def sharded_cf_targets(
     group=None,
     ops: DeviceOps | None = None,
     max_staging_bytes: int = 8 << 30,
+    exchange: PeerExchange | None = None,
 ) -> torch.Tensor:
     """CF targets ``[C, N]`` of ``contracts`` (``[C, 6]`` float64 on the engine's device), with the
     batch dimension sharded over the ranks of ``group``.  Every rank returns the full result."""
@@ -92,6 +140,12 @@ def sharded_cf_targets(
     shard = shard_batches(sp.batches_per_mc_run, world, rank)
     ops = ops or _CabiOps(engine._device, engine._dtype)
     n = contracts.shape[0]
+    if engine._cfg.normalization is ForwardNormalization.RAW and exchange is not None and world > 1:
+        # all-reduce fused into the finalise kernel over peer memory: no collective call on the data path
+        args = engine.fused_args(contracts, n, batch_begin=shard.begin, batch_end=shard.end)
+        out = _cabi.cf_fused_p2p(args, exchange.next_group(), engine._device, engine._dtype)
+        engine.consume(n)
+        return out
     if engine._cfg.normalization is ForwardNormalization.RAW:
         args = engine.fused_args(contracts, n, batch_begin=shard.begin, batch_end=shard.end)
         out = ops.cf_fused(args)

@@ -112,3 +112,68 @@ def test_two_gpu_training_replicas_stay_identical() -> None:
     (_, l0, a0, p0), (_, l1, a1, p1) = results
     assert l0 == l1 and all(np.array_equal(x, y) for x, y in zip(p0, p1))
     assert max(abs(x - y) / abs(y) for x, y in zip(l0, a0)) <= 1e-4  # sharded sums differ from single-GPU sums in the last bits only
+
+
+def _p2p_worker(rank: int, world: int, port: int, prec: str, queue) -> None:
+    import torch.distributed as dist
+
+    from spectralmc_b200.distributed import PeerExchange, sharded_cf_targets
+    from spectralmc_b200.effects import ForwardNormalization, PathScheme
+    from spectralmc_b200.gbm import BlackScholes
+    from spectralmc_b200.numerical import Precision
+    from tests.helpers import expect_success, make_black_scholes_config, make_simulation_params
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        out = {}
+        for N, B, C in ((64, 1001, 3), (48, 37, 700)):  # radix-2 and table-DFT sizes; 700 contracts > one wave of the exchange grid is not needed, but > 1 per CTA stride on small grids
+            sp = make_simulation_params(timesteps=20, network_size=N, batches_per_mc_run=B, mc_seed=5, skip=2, dtype=Precision(prec))
+            cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+            rows = np.tile(np.asarray(ROWS), (C // 3 + 1, 1))[:C]
+            rows[:, 1] *= np.linspace(0.8, 1.2, C)
+            contracts = torch.tensor(rows, dtype=torch.float64, device="cuda")
+            exchange = PeerExchange(C, N)
+            engine = BlackScholes(cfg)
+            fused = [sharded_cf_targets(engine, contracts, exchange=exchange) for _ in range(3)]  # three epochs: both slots reused
+            nccl_engine = BlackScholes(cfg)
+            nccl = [sharded_cf_targets(nccl_engine, contracts) for _ in range(3)]
+            whole = expect_success(BlackScholes(cfg).cf_targets(contracts))
+            torch.cuda.synchronize()
+            assert expect_success(engine.snapshot()).sim_params.skip == 2 + 3 * C
+            out[(N, C)] = ([t.cpu().numpy() for t in fused], [t.cpu().numpy() for t in nccl], whole.cpu().numpy())
+            exchange.close()
+        queue.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("prec", ["float32", "float64"])
+def test_two_gpu_fused_peer_exchange_matches_nccl_and_single_gpu(prec) -> None:
+    """The all-reduce fused into the finalise kernel over peer memory (smc_cf_fused_p2p): complete
+    targets on every rank, bit-identical across ranks, equal to the NCCL route and to one GPU."""
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, prec, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted((queue.get(timeout=240) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    tol = 2e-6 if prec == "float32" else 1e-13
+    for key in results[0][1]:
+        (f0, n0, w0), (f1, n1, w1) = results[0][1][key], results[1][1][key]
+        for step in range(3):
+            assert np.array_equal(f0[step], f1[step]), (key, step)  # every rank forms the identical sum
+            scale = np.max(np.abs(n0[step]))
+            assert np.max(np.abs(f0[step] - n0[step])) <= tol * scale, (key, step)
+        assert np.max(np.abs(f0[0] - w0)) <= tol * np.max(np.abs(w0)), key
+        assert not np.array_equal(f0[0], f0[1])  # later calls consume later normal matrices
