@@ -78,3 +78,27 @@ def test_missing_library_fails_loudly() -> None:
     proc = subprocess.run([sys.executable, "-c", "import spectralmc_b200"], env=env, capture_output=True, text=True)
     assert proc.returncode != 0
     assert "ImportError" in proc.stderr and "no fallback" in proc.stderr
+
+
+def test_peer_exchange_argument_validation_needs_no_device() -> None:
+    from spectralmc_b200 import _cabi
+
+    torch = __import__("torch")
+    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 2) == (2 * 2 * 4 * 16 + 2 * 2 * 4) * 8
+    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 17) == 0  # at most 16 peers
+    args = _cabi.make_fused_args(None, 4, 12, 16, 64, torch.float32, 0, _cabi.SMC_RAW, 42, 0, batch_begin=0, batch_end=32)
+    args.contracts = 16  # any non-NULL value: validation happens before the first device access
+    group = _cabi.P2PGroup()
+    group.rank, group.world, group.capacity_contracts, group.network_size, group.epoch = 0, 2, 4, 16, 0
+    call = lambda: _cabi.LIB.smc_cf_fused_p2p(ctypes.byref(args), ctypes.byref(group), 16, 16, 1 << 20, None)  # noqa: E731
+    assert call() == 1 and b"epoch" in _cabi.LIB.smc_last_error()
+    group.epoch = 1
+    assert call() == 1 and b"buffer of rank 0 is NULL" in _cabi.LIB.smc_last_error()
+    group.buffers[0], group.buffers[1] = 16, 16
+    group.capacity_contracts = 3
+    assert call() == 1 and b"sized for 3 contracts" in _cabi.LIB.smc_last_error()
+    group.capacity_contracts, group.rank = 4, 2
+    assert call() == 1 and b"bad rank" in _cabi.LIB.smc_last_error()
+    group.rank = 0
+    args.normalization = _cabi.SMC_NORMALIZE
+    assert call() == 1 and b"NORMALIZE" in _cabi.LIB.smc_last_error()
