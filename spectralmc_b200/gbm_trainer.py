@@ -42,7 +42,7 @@ from pydantic import BaseModel, ConfigDict
 from torch import nn, optim
 
 from spectralmc_b200.cvnn import FusedCVNN, describe
-from spectralmc_b200.distributed import sharded_cf_targets
+from spectralmc_b200.distributed import PeerExchange, sharded_cf_targets
 from spectralmc_b200.errors import (
     DeviceDTypeError,
     DeviceNotCUDA,
@@ -154,8 +154,8 @@ class GbmCVNNPricer:
     """Trains a CVNN on CF targets produced by the fused Monte-Carlo path."""
 
     @staticmethod
-    def create(cfg: GbmCVNNPricerConfig, *, process_group=None, fused_step: bool | None = None,
-               cuda_graph: bool = True) -> Result["GbmCVNNPricer", DeviceDTypeError | DeviceNotCUDA]:
+    def create(cfg: GbmCVNNPricerConfig, *, process_group=None, fused_step: bool | None = None, cuda_graph: bool = True,
+               peer_exchange: bool = False) -> Result["GbmCVNNPricer", DeviceDTypeError | DeviceNotCUDA]:
         """Validated construction (reference :600-663): the CVNN must live on one CUDA device in the
         simulation's precision."""
         got = _module_device_dtype(cfg.cvnn)
@@ -167,7 +167,7 @@ class GbmCVNNPricer:
         if dtype != cfg.cfg.sim_params.dtype.to_torch():
             return Failure(DeviceDTypeError(message=f"gbm sim dtype {cfg.cfg.sim_params.dtype} does not match cvnn dtype {dtype}"))
         self = GbmCVNNPricer(cfg.cfg, cfg.domain_bounds, cfg.cvnn, sobol_skip=cfg.sobol_skip, global_step=cfg.global_step,
-                             process_group=process_group, fused_step=fused_step, cuda_graph=cuda_graph)
+                             process_group=process_group, fused_step=fused_step, cuda_graph=cuda_graph, peer_exchange=peer_exchange)
         self._optimizer_state = cfg.optimizer_state
         if cfg.torch_cpu_rng_state is not None:  # reference :714-721
             torch.set_rng_state(torch.from_numpy(np.frombuffer(cfg.torch_cpu_rng_state, dtype=np.uint8).copy()))
@@ -176,7 +176,8 @@ class GbmCVNNPricer:
         return Success(self)
 
     def __init__(self, cfg: BlackScholesConfig, domain_bounds: DomainBounds, cvnn: nn.Module, *, sobol_skip: int = 0,
-                 global_step: int = 0, process_group=None, fused_step: bool | None = None, cuda_graph: bool = True) -> None:
+                 global_step: int = 0, process_group=None, fused_step: bool | None = None, cuda_graph: bool = True,
+                 peer_exchange: bool = False) -> None:
         self._cfg, self._sp = cfg, cfg.sim_params
         self._engine = BlackScholes(cfg)
         self._cvnn = cvnn
@@ -185,6 +186,9 @@ class GbmCVNNPricer:
         self._domain_bounds = domain_bounds
         self._sobol_skip, self._global_step = sobol_skip, global_step
         self._group = process_group
+        # multi-GPU RAW runs: fuse the all-reduce of the partial sums into the finalise kernel over peer memory
+        self._want_exchange = peer_exchange and process_group is not None
+        self._exchange: PeerExchange | None = None
         self._optimizer_state: dict | None = None  # Adam state between train() calls (reference :671, :1646)
         supported = describe(cvnn) is not None
         if fused_step and not supported:
@@ -209,7 +213,11 @@ class GbmCVNNPricer:
         """``[C, 6]`` contracts -> ``[C, N]`` complex targets on device (one C-ABI call sequence)."""
         dev = rows if isinstance(rows, torch.Tensor) else self._upload(rows)
         if self._group is not None:
-            return Success(sharded_cf_targets(self._engine, dev, group=self._group))
+            if self._want_exchange and (self._exchange is None or self._exchange.capacity_contracts < dev.shape[0]):
+                if self._exchange is not None:
+                    self._exchange.close()
+                self._exchange = PeerExchange(int(dev.shape[0]), self._sp.network_size, group=self._group)  # collective set-up
+            return Success(sharded_cf_targets(self._engine, dev, group=self._group, exchange=self._exchange))
         return self._engine.cf_targets(dev)
 
     def _torch_step(self, real_in, imag_in, targets, optimizer) -> tuple[torch.Tensor, torch.Tensor]:

@@ -80,7 +80,7 @@ def _train_worker(rank: int, world: int, port: int, queue) -> None:
         cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
         net = make_cvnn(6, 16, seed=9, device=f"cuda:{rank}")
         pc = expect_success(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=net))
-        trainer = expect_success(GbmCVNNPricer.create(pc, process_group=dist.group.WORLD))
+        trainer = expect_success(GbmCVNNPricer.create(pc, process_group=dist.group.WORLD, peer_exchange=True))
         result = expect_success(trainer.train(expect_success(build_training_config(num_batches=3, batch_size=16, learning_rate=1e-2))))
         single = expect_success(GbmCVNNPricer.create(expect_success(build_gbm_cvnn_pricer_config(
             cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=make_cvnn(6, 16, seed=9, device=f"cuda:{rank}")))))
@@ -93,8 +93,9 @@ def _train_worker(rank: int, world: int, port: int, queue) -> None:
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpu_training_replicas_stay_identical() -> None:
-    """Batch rows sharded over two ranks, targets all-reduced, each rank steps its own CVNN replica
-    through the fused step: the replicas stay bit-identical and track the single-GPU run."""
+    """Batch rows sharded over two ranks, partial sums exchanged inside the finalise kernel over peer
+    memory, each rank steps its own CVNN replica through the fused step: the replicas stay
+    bit-identical and track the single-GPU run."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
