@@ -241,6 +241,11 @@ def run_b200(args) -> None:
     def step_e2e(step: int):
         if world == 1:
             _cabi.cf_fused_host(make_args(step, None), contracts_pin, out_pin, ws)  # H2D + kernels + D2H + sync
+        elif exchange is not None and contracts_pin.numel() * 8 <= 65536 and out_pin.numel() * out_pin.element_size() <= 65536:
+            # small pinned buffers: the kernels read the contracts and write the targets through the buffers'
+            # device aliases (as smc_cf_fused_host does on one GPU) — no staging copies
+            _cabi.cf_fused_p2p(make_args(step, contracts_pin), exchange.next_group(), dev, dtype, ws, out=out_pin)
+            torch.cuda.current_stream().synchronize()
         else:
             cdev = contracts_pin.to(dev, non_blocking=True)
             out = sharded(step, cdev)
@@ -295,7 +300,10 @@ def run_b200(args) -> None:
         "cf_estimates_per_sec": C * args.steps / (ms_dev * 1e-3),
         "e2e": {"value": e2e_value, "unit": "path-steps/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(contracts_pin.numel() * 8), "d2h_bytes_per_step": int(out_pin.numel() * out_pin.element_size()),
-                "api": "smc_cf_fused_host (C ABI, pinned host buffers)" if world == 1 else f"H2D + sharded fused path [{collective}] + D2H"},
+                "api": "smc_cf_fused_host (C ABI, pinned host buffers)" if world == 1 else
+                       (f"smc_cf_fused_p2p on pinned host buffers (contracts read and targets written through their device aliases) [{collective}]"
+                        if exchange is not None and contracts_pin.numel() * 8 <= 65536 and out_pin.numel() * out_pin.element_size() <= 65536
+                        else f"H2D + sharded fused path [{collective}] + D2H")},
         "gpu_launches": launches["n"], "clocks": clk,
     }
 

@@ -516,9 +516,12 @@ def p2p_open(handle: bytes) -> int:
 
 
 def cf_fused_p2p(args: FusedArgs, group: P2PGroup, device: torch.device, dtype: torch.dtype,
-                 workspace: torch.Tensor | None = None) -> torch.Tensor:
-    """Sharded fused batch path with the all-reduce fused into the finalise kernel: COMPLETE targets on every rank."""
-    out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=device)
+                 workspace: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Sharded fused batch path with the all-reduce fused into the finalise kernel: COMPLETE targets on every rank.
+    ``out`` may be a pinned host tensor (device-addressable under unified addressing): the kernel then writes the
+    targets straight to host memory."""
+    if out is None:
+        out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=device)
     need = LIB.smc_cf_fused_workspace_bytes(byref(args))
     ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, device)
     check(LIB.smc_cf_fused_p2p(byref(args), byref(group), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
