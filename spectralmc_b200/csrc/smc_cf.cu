@@ -305,13 +305,16 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #ifndef SMC_F32_FUSED_MIN_CTAS_OTHER
 #define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
 #endif
+#ifndef SMC_F32_FUSED_MIN_CTAS_TERMINAL
+#define SMC_F32_FUSED_MIN_CTAS_TERMINAL 4  // log-Euler with staged terminals (NORMALIZE pass A): 1.360 ms at c2 vs 1.445 at 5
+#endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
 #define SMC_F32_FUSED_MIN_CTAS 5  // with SMC_F32X2=1: measured best (1.322 ms vs 1.385 at 4, 1.341 at 6; profiles/r1_codegen_variant_matrix.txt)
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
 template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
-__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : ((SCHEME == SMC_LOG_EULER && OUT == OUT_COLSUM) ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_OTHER)))
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER)))
     tile_kernel(const TileParams p) {
   __shared__ double sm[CF_BLOCK];
   const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
@@ -430,7 +433,8 @@ __global__ void __launch_bounds__(CF_BLOCK)
   __shared__ double sm[32];
   const int64_t c = blockIdx.x;
   double s = 0.0;
-  for (int64_t t = threadIdx.x; t < tiles; t += CF_BLOCK) s += term_partial[c * tiles + t];
+  if (threadIdx.x < tiles)  // this thread's tiles: threadIdx.x, threadIdx.x + 256, ... (eight loads in flight)
+    s = strided_sum(term_partial + c * tiles + threadIdx.x, (tiles - threadIdx.x + CF_BLOCK - 1) / CF_BLOCK, CF_BLOCK);
   const double tot = block_sum(s, sm);
   if (threadIdx.x == 0) out[c] = tot;
 }
