@@ -197,6 +197,9 @@ class GbmCVNNPricer:
         self._use_graph = cuda_graph
         self._fused: FusedCVNN | None = None
         self._graphs: dict[int, _StepGraph] = {}
+        self._staging: dict[tuple, list] = {}
+        self._staging_next = 0
+        self._nn_stream: torch.cuda.Stream | None = None  # CVNN steps run here, one step behind the simulation
         # the sampler is seeded with mc_seed and resumed with sobol_skip (reference :703-710)
         self._sampler_result = SobolSampler.create(BlackScholes.Inputs, domain_bounds, config=SobolConfig(seed=self._sp.mc_seed, skip=sobol_skip))
 
@@ -206,8 +209,21 @@ class GbmCVNNPricer:
         return self._engine.simulate_fft(contract)
 
     def _upload(self, rows: np.ndarray) -> torch.Tensor:
-        host = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64)).pin_memory()
-        return host.to(self._device, non_blocking=True)
+        """Contracts -> device through a small ring of reusable pinned staging buffers (a slot is rewritten
+        only after the copy that last read it has completed)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float64)
+        ring = self._staging.get(rows.shape)
+        if ring is None:
+            ring = self._staging[rows.shape] = [[torch.empty(rows.shape, dtype=torch.float64).pin_memory(), None] for _ in range(4)]
+        slot = ring[self._staging_next % len(ring)]
+        self._staging_next += 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0].numpy()[...] = rows
+        dev = slot[0].to(self._device, non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
+        return dev
 
     def targets(self, rows: np.ndarray | torch.Tensor) -> Result[torch.Tensor, object]:
         """``[C, 6]`` contracts -> ``[C, N]`` complex targets on device (one C-ABI call sequence)."""
@@ -278,6 +294,17 @@ class GbmCVNNPricer:
         self._cvnn.train()
         losses = torch.zeros(max(config.num_batches, 1), dtype=torch.float64, device=self._device)
         grad_norm: torch.Tensor | None = None
+        # Software pipeline (fused route, no per-step logger): the CVNN step of batch i is issued on a second
+        # stream and overlaps the simulation of batch i + 1 — the two are independent, and the step's small
+        # launches fit into the SM slots the tile kernel frees.  Same kernels in the same per-stream order, so
+        # results are bit-identical to the serial schedule.
+        pipelined = self._use_fused and logger is None
+        sim_stream = torch.cuda.current_stream(self._device)
+        if pipelined:
+            if self._nn_stream is None:
+                # high priority: the step's small CTAs take SM slots as soon as the simulation kernel frees any
+                self._nn_stream = torch.cuda.Stream(self._device, priority=-1)
+            self._nn_stream.wait_stream(sim_stream)  # parameters / optimiser state produced so far
         for i in range(config.num_batches):
             t0 = time.perf_counter()
             drawn = sampler.sample_array(config.batch_size)
@@ -291,7 +318,15 @@ class GbmCVNNPricer:
                 return got
             targets = got.value.detach()  # already a torch tensor: the DLPack hand-off is the identity
             with _nvtx("smc.cvnn_step"):
-                if self._use_fused:
+                if pipelined:
+                    ready = torch.cuda.Event()
+                    ready.record(sim_stream)
+                    with torch.cuda.stream(self._nn_stream):
+                        self._nn_stream.wait_event(ready)
+                        contracts.record_stream(self._nn_stream)  # allocated on the simulation stream, read here
+                        targets.record_stream(self._nn_stream)
+                        self._fused_step(contracts, targets, losses[i : i + 1])
+                elif self._use_fused:
                     self._fused_step(contracts, targets, losses[i : i + 1])
                 else:
                     real_in = contracts.to(self._dtype)
@@ -302,6 +337,8 @@ class GbmCVNNPricer:
                 gn = self._fused.grads.norm() if self._use_fused else grad_norm
                 logger(StepMetrics(step=self._global_step, batch_time=time.perf_counter() - t0, loss=float(losses[i]),
                                    grad_norm=float(gn), lr=config.learning_rate, optimizer=optimizer, model=self._cvnn))
+        if pipelined:
+            sim_stream.wait_stream(self._nn_stream)
         if config.num_batches > 0:
             grad_norm = self._fused.grads.norm() if self._use_fused else grad_norm
         host = [float(x) for x in losses[: config.num_batches].cpu()]
@@ -379,7 +416,9 @@ class _StepGraph:
         fused.warm_up(rows)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # captured on a high-priority stream: kernel nodes keep that priority, so a replay that overlaps the next
+        # simulation gets SM slots as soon as the big kernel frees any (see GbmCVNNPricer.train)
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(dev, priority=-1)):
             fused.train_step(self.real_in, self.imag_in, self.targets, self.loss)
 
 
