@@ -203,7 +203,7 @@ int smc_cf_from_terminal(const smc_fused_args* args, const void* terminal,
  * finished allocating and opening before the first call (a barrier of the caller's process group).
  * `epoch` must be > 0, equal on all ranks for one call and strictly increasing from call to call;
  * all ranks must make the same sequence of calls on one stream each.  A peer that never arrives
- * makes the kernel trap after 2^26 polls, about a minute (CUDA error at the next synchronisation, no hang).
+ * makes the kernel trap after 2^27 polls, about a minute (CUDA error at the next synchronisation, no hang).
  */
 typedef struct smc_p2p_group {
   int rank;

@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(CF_BLOCK)
 // every CTA finishes phase 1 (which never waits) for all of its contracts before it waits in phase 2,
 // so every flag a peer waits for is written by a CTA that is already running.  Slots alternate with the
 // epoch parity: a rank can be at most one call ahead of a peer, because its phase 2 of call k needs
-// that peer's phase 1 of call k.  A wait that exceeds 2^26 polls (about a minute) traps: a diagnosable error, not a hang.
+// that peer's phase 1 of call k.  A wait that exceeds 2^27 polls (about a minute) traps: a diagnosable error, not a hang.
 constexpr int MAX_PEERS = 16;
 
 struct PeerExchange {
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(CF_BLOCK)
       const unsigned* flag = reinterpret_cast<const unsigned*>(mine + flag_base + ((slot * px.world + threadIdx.x) * cap + c));
       unsigned polls = 0;
       while (load_acquire_sys(flag) != px.epoch)
-        if (++polls > (1u << 26)) __trap();  // about a minute of polling: the peer is gone
+        if (++polls > (1u << 27)) __trap();  // about a minute of polling: the peer is gone
     }
     __syncthreads();
     for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
