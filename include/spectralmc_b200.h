@@ -12,8 +12,9 @@
  *     available from smc_last_error() (thread-local).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All
  *     work is stream-ordered; no function synchronises the host unless its name ends in
- *     `_host`.  The library never allocates device memory: scratch space is a caller-
- *     provided workspace whose size comes from the matching *_workspace_bytes().
+ *     `_host`.  Scratch space is a caller-provided workspace whose size comes from the matching
+ *     *_workspace_bytes(); the library allocates device memory only in smc_p2p_alloc (peer
+ *     exchange buffers have to come from cudaMalloc to be exportable over cudaIpc).
  *   - `dtype`: SMC_F32 / SMC_F64 (the reference's Precision.float32/float64,
  *     models/numerical.py:124-130).  Complex outputs are interleaved (re, im) pairs of the
  *     same width (complex64 / complex128).
