@@ -223,6 +223,16 @@ int smc_p2p_free(void* ptr);
 int smc_cf_fused_p2p(const smc_fused_args* args, const smc_p2p_group* group, void* cf_out,
                      void* workspace /* smc_cf_fused_workspace_bytes(args) */, size_t workspace_bytes,
                      void* stream);
+/* NORMALIZE over several GPUs on the same buffers (one epoch covers both exchanges of a step):
+ *   smc_fused_terminal  ->  smc_p2p_allreduce_sum_f64(terminal_sum, n_contracts)  ->  smc_cf_from_terminal_p2p
+ * smc_p2p_allreduce_sum_f64 sums `count` (<= capacity_contracts) device doubles over the ranks in place, in rank
+ * order (identical bits everywhere); smc_cf_from_terminal_p2p is smc_cf_from_terminal with the final exchange
+ * fused into the finalise kernel (complete targets on every rank). */
+int smc_p2p_allreduce_sum_f64(double* inout, int64_t count, const smc_p2p_group* group, void* stream);
+int smc_cf_from_terminal_p2p(const smc_fused_args* args, const smc_p2p_group* group, const void* terminal,
+                             const double* terminal_sum_global /* device double[C] or NULL */, void* cf_out,
+                             void* workspace /* smc_cf_from_terminal_workspace_bytes(args) */,
+                             size_t workspace_bytes, void* stream);
 
 /* Host-buffer convenience for the reference-facing call: copies `contracts_host`
  * (ideally pinned) to the device, runs smc_cf_fused, copies the [n_contracts, N] complex

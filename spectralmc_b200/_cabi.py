@@ -34,7 +34,8 @@ EXPORTS = (
     "smc_cf_fused_host smc_pipe_calibrate "
     "smc_cvnn_workspace_bytes smc_cvnn_output_width smc_cvnn_forward smc_cvnn_loss_backward smc_adam_step "
     "smc_cvnn_train_step "
-    "smc_p2p_buffer_bytes smc_p2p_alloc smc_p2p_open smc_p2p_close smc_p2p_free smc_cf_fused_p2p"
+    "smc_p2p_buffer_bytes smc_p2p_alloc smc_p2p_open smc_p2p_close smc_p2p_free smc_cf_fused_p2p "
+    "smc_p2p_allreduce_sum_f64 smc_cf_from_terminal_p2p"
 ).split()
 
 SMC_LAYER_LINEAR, SMC_LAYER_MODRELU, SMC_LAYER_ZRELU = 0, 1, 2
@@ -159,6 +160,8 @@ def _load() -> ctypes.CDLL:
     lib.smc_p2p_close.argtypes = [c_void_p]
     lib.smc_p2p_free.argtypes = [c_void_p]
     lib.smc_cf_fused_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.smc_p2p_allreduce_sum_f64.argtypes = [c_void_p, c_int64, POINTER(P2PGroup), c_void_p]
+    lib.smc_cf_from_terminal_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cvnn_workspace_bytes.argtypes = [POINTER(CvnnNet), c_int64, c_int]
     lib.smc_cvnn_output_width.argtypes = [POINTER(CvnnNet)]
     lib.smc_cvnn_output_width.restype = c_int64
@@ -525,4 +528,23 @@ def cf_fused_p2p(args: FusedArgs, group: P2PGroup, device: torch.device, dtype: 
     need = LIB.smc_cf_fused_workspace_bytes(byref(args))
     ws = workspace if workspace is not None and workspace.numel() >= need else _workspace(need, device)
     check(LIB.smc_cf_fused_p2p(byref(args), byref(group), out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out
+
+
+def p2p_allreduce_sum_f64(values: torch.Tensor, group: P2PGroup) -> None:
+    """In-place sum over ranks of a float64 device vector through the exchange buffers (no collective call)."""
+    _require_cuda(values, "values")
+    if values.dtype != torch.float64:
+        raise TypeError("values must be float64")
+    check(LIB.smc_p2p_allreduce_sum_f64(values.data_ptr(), values.numel(), byref(group), _stream()))
+
+
+def cf_from_terminal_p2p(args: FusedArgs, group: P2PGroup, terminal: torch.Tensor, terminal_sum_global: torch.Tensor | None,
+                         dtype: torch.dtype) -> torch.Tensor:
+    _require_cuda(terminal, "terminal")
+    out = torch.empty((args.n_contracts, args.network_size), dtype=complex_dtype(dtype), device=terminal.device)
+    ws = _workspace(LIB.smc_cf_from_terminal_workspace_bytes(byref(args)), terminal.device)
+    tsum_ptr = terminal_sum_global.data_ptr() if terminal_sum_global is not None else None
+    check(LIB.smc_cf_from_terminal_p2p(byref(args), byref(group), terminal.data_ptr(), tsum_ptr, out.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), _stream()))
     return out

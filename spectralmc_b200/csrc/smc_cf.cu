@@ -570,8 +570,20 @@ struct PeerExchange {
   int64_t capacity_contracts;  // contracts the buffers were sized for
 };
 
+// Exchange buffer of one rank, in 8-byte cells:
+//   [2 slots][world senders][capacity contracts][n]   partial column sums          (exchange-finalise kernel)
+//   [2 slots][world senders][capacity contracts]      their per-contract flags
+//   [2 slots][world senders][capacity contracts]      one double per contract      (small all-reduce: terminal sums)
+//   [2 slots][world senders]                          its per-sender flags
 __host__ __device__ inline size_t exchange_data_doubles(int64_t capacity_contracts, int64_t n, int world) {
   return static_cast<size_t>(2) * world * capacity_contracts * n;
+}
+__host__ __device__ inline size_t exchange_small_base(int64_t capacity_contracts, int64_t n, int world) {
+  return exchange_data_doubles(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts;
+}
+__host__ __device__ inline size_t exchange_total_cells(int64_t capacity_contracts, int64_t n, int world) {
+  return exchange_small_base(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts +
+         static_cast<size_t>(2) * world;
 }
 
 __device__ __forceinline__ void store_release_sys(unsigned* p, unsigned v) {
@@ -633,6 +645,37 @@ __global__ void __launch_bounds__(CF_BLOCK)
     __syncthreads();
     transform_store<Real>(re, im, twr, twi, n, mode, out + c * n * 2);
     __syncthreads();  // re / im are reused by the next contract of this CTA
+  }
+}
+
+// In-place sum over ranks of `count` doubles (count <= capacity contracts) through the small region of the
+// exchange buffers: push to every peer, publish one flag per peer, wait for all senders, sum in rank order.
+// One CTA (the vector is at most a few thousand doubles); used for the NORMALIZE terminal sums.
+__global__ void __launch_bounds__(CF_BLOCK)
+    p2p_allreduce_small_kernel(double* __restrict__ inout, int64_t count, int64_t n, const PeerExchange px) {
+  const int64_t cap = px.capacity_contracts;
+  const int64_t slot = px.epoch & 1u;
+  const size_t base = exchange_small_base(cap, n, px.world);
+  const size_t flags = base + static_cast<size_t>(2) * px.world * cap;
+  for (int64_t i = threadIdx.x; i < count; i += CF_BLOCK) {
+    const double v = inout[i];
+    for (int p = 0; p < px.world; ++p) px.data[p][base + (slot * px.world + px.rank) * cap + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < px.world) {
+    store_release_sys(reinterpret_cast<unsigned*>(px.data[threadIdx.x] + flags + slot * px.world + px.rank), px.epoch);
+    const unsigned* flag = reinterpret_cast<const unsigned*>(px.data[px.rank] + flags + slot * px.world + threadIdx.x);
+    unsigned polls = 0;
+    while (load_acquire_sys(flag) != px.epoch)
+      if (++polls > (1u << 27)) __trap();
+  }
+  __syncthreads();
+  const double* mine = px.data[px.rank] + base;
+  for (int64_t i = threadIdx.x; i < count; i += CF_BLOCK) {
+    double s = 0.0;
+    for (int q = 0; q < px.world; ++q) s += __ldcv(mine + (slot * px.world + q) * cap + i);
+    inout[i] = s;
   }
 }
 
@@ -891,8 +934,7 @@ extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, siz
 // ---- batch-sharded RAW with the all-reduce fused into the finalise kernel (peer memory) ------------
 extern "C" size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world) {
   if (capacity_contracts <= 0 || network_size <= 0 || world <= 0 || world > MAX_PEERS) return 0;
-  return (exchange_data_doubles(capacity_contracts, network_size, world) +
-          static_cast<size_t>(2) * world * capacity_contracts) * sizeof(double);
+  return exchange_total_cells(capacity_contracts, network_size, world) * sizeof(double);
 }
 
 extern "C" int smc_p2p_alloc(size_t bytes, void** ptr, void* handle64) {
@@ -927,6 +969,59 @@ extern "C" int smc_p2p_free(void* ptr) {
   return SMC_OK;
 }
 
+static PeerExchange make_peer_exchange(const smc_p2p_group* g) {
+  PeerExchange px{};
+  for (int q = 0; q < g->world; ++q) px.data[q] = static_cast<double*>(g->buffers[q]);
+  px.rank = g->rank;
+  px.world = g->world;
+  px.epoch = g->epoch;
+  px.capacity_contracts = g->capacity_contracts;
+  return px;
+}
+
+static int check_group(const char* fn, const smc_fused_args* a, const smc_p2p_group* g) {
+  SMC_REQUIRE(g != nullptr, "%s: group is NULL", fn);
+  SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world, "%s: bad rank %d of %d", fn,
+              g->rank, g->world);
+  SMC_REQUIRE(g->epoch > 0, "%s: epoch must be > 0 (zero marks an unwritten flag)", fn);
+  SMC_REQUIRE(a->n_contracts <= g->capacity_contracts && a->network_size == g->network_size,
+              "%s: exchange buffers sized for %lld contracts x %lld, call has %lld x %lld", fn,
+              (long long)g->capacity_contracts, (long long)g->network_size, (long long)a->n_contracts,
+              (long long)a->network_size);
+  for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "%s: buffer of rank %d is NULL", fn, q);
+  return SMC_OK;
+}
+
+// tile partials -> (optional level 1) -> persistent exchange + finalise kernel
+template <typename Real>
+static int reduce_and_exchange_finalize(const TilePlan& plan, const FinalizePlan& f, double* partial, double* grouped,
+                                        const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, cudaStream_t st) {
+  const int64_t n = a->network_size;
+  const double* vecs = partial;
+  int64_t groups = plan.tiles;
+  if (plan.tiles > MAX_GROUPS) {
+    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
+    reduce_tiles_kernel<<<static_cast<unsigned>(plan.groups * a->n_contracts), CF_BLOCK, 0, st>>>(
+        partial, grouped, plan.tiles, plan.tiles_per_group, plan.groups, n, subs);
+    SMC_LAUNCH_OK("reduce_tiles_kernel");
+    vecs = grouped;
+    groups = plan.groups;
+  }
+  if (f.smem > 48 * 1024)
+    SMC_CUDA_OK(cudaFuncSetAttribute(cf_exchange_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(f.smem)));
+  int per_sm = 0;
+  SMC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf_exchange_finalize_kernel<Real>, CF_BLOCK, f.smem));
+  const int64_t resident = static_cast<int64_t>(per_sm) * sm_count();
+  SMC_REQUIRE(resident > 0, "peer exchange: the exchange kernel does not fit on an SM");
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(a->n_contracts, resident));  // co-resident: see the kernel
+  cf_exchange_finalize_kernel<Real><<<grid, CF_BLOCK, f.smem, st>>>(
+      vecs, groups, n, 1.0 / static_cast<double>(a->batches_total), f.mode, f.log2n, static_cast<Real*>(cf_out),
+      a->n_contracts, make_peer_exchange(g));
+  SMC_LAUNCH_OK("cf_exchange_finalize_kernel");
+  return SMC_OK;
+}
+
 template <typename Real>
 static int cf_fused_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
                              cudaStream_t st) {
@@ -943,35 +1038,7 @@ static int cf_fused_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, vo
   SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
   double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
   if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
-  const double* vecs = p.partial;
-  int64_t groups = plan.tiles;
-  if (plan.tiles > MAX_GROUPS) {
-    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
-    reduce_tiles_kernel<<<static_cast<unsigned>(plan.groups * a->n_contracts), CF_BLOCK, 0, st>>>(
-        p.partial, grouped, plan.tiles, plan.tiles_per_group, plan.groups, n, subs);
-    SMC_LAUNCH_OK("reduce_tiles_kernel");
-    vecs = grouped;
-    groups = plan.groups;
-  }
-  if (f.smem > 48 * 1024)
-    SMC_CUDA_OK(cudaFuncSetAttribute(cf_exchange_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(f.smem)));
-  int per_sm = 0;
-  SMC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf_exchange_finalize_kernel<Real>, CF_BLOCK, f.smem));
-  const int64_t resident = static_cast<int64_t>(per_sm) * sm_count();
-  SMC_REQUIRE(resident > 0, "smc_cf_fused_p2p: the exchange kernel does not fit on an SM");
-  PeerExchange px{};
-  for (int q = 0; q < g->world; ++q) px.data[q] = static_cast<double*>(g->buffers[q]);
-  px.rank = g->rank;
-  px.world = g->world;
-  px.epoch = g->epoch;
-  px.capacity_contracts = g->capacity_contracts;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(a->n_contracts, resident));  // co-resident: see the kernel
-  cf_exchange_finalize_kernel<Real><<<grid, CF_BLOCK, f.smem, st>>>(
-      vecs, groups, n, 1.0 / static_cast<double>(a->batches_total), f.mode, f.log2n, static_cast<Real*>(cf_out),
-      a->n_contracts, px);
-  SMC_LAUNCH_OK("cf_exchange_finalize_kernel");
-  return SMC_OK;
+  return reduce_and_exchange_finalize<Real>(plan, f, p.partial, grouped, a, g, cf_out, st);
 }
 
 extern "C" int smc_cf_fused_p2p(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
@@ -981,13 +1048,7 @@ extern "C" int smc_cf_fused_p2p(const smc_fused_args* a, const smc_p2p_group* g,
   SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr && ws != nullptr && g != nullptr, "smc_cf_fused_p2p: NULL pointer");
   SMC_REQUIRE(a->normalization == SMC_RAW,
               "smc_cf_fused_p2p: NORMALIZE needs the global terminal mean first (smc_fused_terminal + allreduce + smc_cf_from_terminal)");
-  SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world, "smc_cf_fused_p2p: bad rank %d of %d",
-              g->rank, g->world);
-  SMC_REQUIRE(g->epoch > 0, "smc_cf_fused_p2p: epoch must be > 0 (zero marks an unwritten flag)");
-  SMC_REQUIRE(a->n_contracts <= g->capacity_contracts && a->network_size == g->network_size,
-              "smc_cf_fused_p2p: exchange buffers sized for %lld contracts x %lld, call has %lld x %lld",
-              (long long)g->capacity_contracts, (long long)g->network_size, (long long)a->n_contracts, (long long)a->network_size);
-  for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "smc_cf_fused_p2p: buffer of rank %d is NULL", q);
+  if (int e = check_group("smc_cf_fused_p2p", a, g)) return e;
   return a->dtype == SMC_F32 ? cf_fused_p2p_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
                              : cf_fused_p2p_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
 }
@@ -1064,6 +1125,55 @@ extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* termina
   return a->dtype == SMC_F32
              ? cf_from_terminal_impl<float>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
              : cf_from_terminal_impl<double>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
+}
+
+// NORMALIZE over several GPUs without a collective call: smc_fused_terminal, then this in-place sum over
+// ranks of the per-contract terminal sums, then smc_cf_from_terminal_p2p.
+extern "C" int smc_p2p_allreduce_sum_f64(double* inout, int64_t count, const smc_p2p_group* g, void* stream) {
+  clear_error();
+  SMC_REQUIRE(inout != nullptr && g != nullptr && count > 0, "smc_p2p_allreduce_sum_f64: bad argument");
+  SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world,
+              "smc_p2p_allreduce_sum_f64: bad rank %d of %d", g->rank, g->world);
+  SMC_REQUIRE(g->epoch > 0 && count <= g->capacity_contracts, "smc_p2p_allreduce_sum_f64: %lld values, buffers hold %lld (epoch %u)",
+              (long long)count, (long long)g->capacity_contracts, g->epoch);
+  for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "smc_p2p_allreduce_sum_f64: buffer of rank %d is NULL", q);
+  p2p_allreduce_small_kernel<<<1, CF_BLOCK, 0, as_stream(stream)>>>(inout, count, g->network_size, make_peer_exchange(g));
+  SMC_LAUNCH_OK("p2p_allreduce_small_kernel");
+  return SMC_OK;
+}
+
+template <typename Real>
+static int cf_from_terminal_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal, const double* tsum,
+                                     void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int64_t n = a->network_size;
+  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n, true);
+  const FinalizePlan f = finalize_plan(n);
+  if (f.mode == 2) return set_error(SMC_EUNSUPPORTED, "smc_cf_from_terminal_p2p: network_size %lld needs the spill transform", (long long)n);
+  if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
+    return set_error(SMC_EWORKSPACE, "smc_cf_from_terminal_p2p: workspace too small");
+  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
+  TileParams p = base_params(a, plan);
+  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
+  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
+  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
+  p.terminal_in = terminal;
+  p.terminal_sum = tsum;
+  p.normalize = tsum != nullptr;
+  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
+  return reduce_and_exchange_finalize<Real>(plan, f, p.partial, grouped, a, g, cf_out, st);
+}
+
+extern "C" int smc_cf_from_terminal_p2p(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal,
+                                        const double* tsum, void* cf_out, void* ws, size_t ws_bytes, void* stream) {
+  clear_error();
+  if (int e = check_args("smc_cf_from_terminal_p2p", a)) return e;
+  SMC_REQUIRE(a->contracts && terminal && cf_out && ws, "smc_cf_from_terminal_p2p: NULL pointer");
+  SMC_REQUIRE((a->normalization == SMC_NORMALIZE) == (tsum != nullptr),
+              "smc_cf_from_terminal_p2p: terminal_sum_global must be given iff normalization is NORMALIZE");
+  if (int e = check_group("smc_cf_from_terminal_p2p", a, g)) return e;
+  return a->dtype == SMC_F32
+             ? cf_from_terminal_p2p_impl<float>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
+             : cf_from_terminal_p2p_impl<double>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
 }
 
 // ---- materialised payoff matrix -> CF -------------------------------------------------------

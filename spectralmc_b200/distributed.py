@@ -160,9 +160,14 @@ def sharded_cf_targets(
         part = contracts[c0 : c0 + chunk].contiguous()
         args = engine.fused_args(part, part.shape[0], batch_begin=shard.begin, batch_end=shard.end)
         terminal, tsum = ops.fused_terminal(args)
-        _all_reduce_sum(tsum, group)
-        out = ops.cf_from_terminal(args, terminal, tsum)
-        _all_reduce_sum(out, group)
+        if exchange is not None and world > 1:  # both exchanges of the step through peer memory, one epoch
+            pg = exchange.next_group()
+            _cabi.p2p_allreduce_sum_f64(tsum, pg)
+            out = _cabi.cf_from_terminal_p2p(args, pg, terminal, tsum, engine._dtype)
+        else:
+            _all_reduce_sum(tsum, group)
+            out = ops.cf_from_terminal(args, terminal, tsum)
+            _all_reduce_sum(out, group)
         engine.consume(part.shape[0])
         outs.append(out)
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)

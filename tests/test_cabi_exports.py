@@ -84,7 +84,8 @@ def test_peer_exchange_argument_validation_needs_no_device() -> None:
     from spectralmc_b200 import _cabi
 
     torch = __import__("torch")
-    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 2) == (2 * 2 * 4 * 16 + 2 * 2 * 4) * 8
+    # data + per-contract flags + small all-reduce region + its flags, in 8-byte cells
+    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 2) == (2 * 2 * 4 * 16 + 2 * 2 * 4 + 2 * 2 * 4 + 2 * 2) * 8
     assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 17) == 0  # at most 16 peers
     args = _cabi.make_fused_args(None, 4, 12, 16, 64, torch.float32, 0, _cabi.SMC_RAW, 42, 0, batch_begin=0, batch_end=32)
     args.contracts = 16  # any non-NULL value: validation happens before the first device access

@@ -115,7 +115,7 @@ def test_two_gpu_training_replicas_stay_identical() -> None:
     assert max(abs(x - y) / abs(y) for x, y in zip(l0, a0)) <= 1e-4  # sharded sums differ from single-GPU sums in the last bits only
 
 
-def _p2p_worker(rank: int, world: int, port: int, prec: str, queue) -> None:
+def _p2p_worker(rank: int, world: int, port: int, prec: str, queue, norm: str = "raw_paths") -> None:
     import torch.distributed as dist
 
     from spectralmc_b200.distributed import PeerExchange, sharded_cf_targets
@@ -131,7 +131,7 @@ def _p2p_worker(rank: int, world: int, port: int, prec: str, queue) -> None:
         out = {}
         for N, B, C in ((64, 1001, 3), (48, 37, 700)):  # radix-2 and table-DFT sizes; 700 contracts > one wave of the exchange grid is not needed, but > 1 per CTA stride on small grids
             sp = make_simulation_params(timesteps=20, network_size=N, batches_per_mc_run=B, mc_seed=5, skip=2, dtype=Precision(prec))
-            cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+            cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization(norm))
             rows = np.tile(np.asarray(ROWS), (C // 3 + 1, 1))[:C]
             rows[:, 1] *= np.linspace(0.8, 1.2, C)
             contracts = torch.tensor(rows, dtype=torch.float64, device="cuda")
@@ -151,10 +151,12 @@ def _p2p_worker(rank: int, world: int, port: int, prec: str, queue) -> None:
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("norm", ["raw_paths", "normalize_forwards"])
 @pytest.mark.parametrize("prec", ["float32", "float64"])
-def test_two_gpu_fused_peer_exchange_matches_nccl_and_single_gpu(prec) -> None:
-    """The all-reduce fused into the finalise kernel over peer memory (smc_cf_fused_p2p): complete
-    targets on every rank, bit-identical across ranks, equal to the NCCL route and to one GPU."""
+def test_two_gpu_fused_peer_exchange_matches_nccl_and_single_gpu(prec, norm) -> None:
+    """The all-reduce fused into the finalise kernel over peer memory (smc_cf_fused_p2p; for NORMALIZE
+    smc_p2p_allreduce_sum_f64 + smc_cf_from_terminal_p2p): complete targets on every rank, bit-identical
+    across ranks, equal to the NCCL route and to one GPU."""
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -162,7 +164,7 @@ def test_two_gpu_fused_peer_exchange_matches_nccl_and_single_gpu(prec) -> None:
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
-    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, prec, queue)) for r in range(2)]
+    procs = [ctx.Process(target=_p2p_worker, args=(r, 2, port, prec, queue, norm)) for r in range(2)]
     for p in procs:
         p.start()
     results = sorted((queue.get(timeout=240) for _ in range(2)), key=lambda t: t[0])
