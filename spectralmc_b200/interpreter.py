@@ -58,12 +58,28 @@ class TensorRegistry:
         t = self._tensors.get(tensor_id)
         return Success(t) if t is not None else Failure(f"unknown tensor {tensor_id!r}")
 
-    def register_kernel(self, name: str, fn: Callable[..., object]) -> None:
+    def get_torch_tensor(self, tensor_id: str) -> Result[torch.Tensor, str]:
+        """Reference name (effects/registry.py:208); tensors here ARE torch tensors."""
+        return self.get_tensor(tensor_id)
+
+    def has_tensor(self, tensor_id: str) -> bool:
+        return tensor_id in self._tensors
+
+    def register_kernel(self, name: str, fn: Callable[..., object]) -> Result[None, str]:
+        if not name:
+            return Failure("empty kernel name")
         self._kernels[name] = fn
+        return Success(None)
 
     def get_kernel(self, name: str) -> Result[Callable[..., object], str]:
         k = self._kernels.get(name)
         return Success(k) if k is not None else Failure(f"unknown kernel {name!r}")
+
+    def has_kernel(self, name: str) -> bool:
+        return name in self._kernels
+
+    def clear_tensors(self) -> None:
+        self._tensors.clear()
 
 
 class MonteCarloOperators:
@@ -124,3 +140,8 @@ class MonteCarloOperators:
         if t.dim() != 2 or axis != 1 or t.is_complex():
             return Failure(MonteCarloError(message="ComputeFFT supports a real 2-D tensor transformed along its last axis"))
         return self._store(effect.output_tensor_id, _cabi.fft_rows(t.contiguous()))
+
+
+# the reference's names for the two classes (effects/registry.py:95, effects/interpreter.py:537)
+SharedRegistry = TensorRegistry
+MonteCarloInterpreter = MonteCarloOperators

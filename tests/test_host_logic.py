@@ -154,3 +154,21 @@ def test_pricer_create_rejects_a_cpu_model_without_touching_the_device() -> None
     got = GbmCVNNPricer.create(pc.value.model_copy(update={"cvnn": mixed}))
     assert isinstance(got, Failure) and isinstance(got.error, DeviceDTypeError)
     assert isinstance(build_gbm_cvnn_pricer_config(cfg=cfg, domain_bounds=make_domain_bounds(), cvnn=mixed, bogus=1), Failure)
+
+
+def test_registry_mirrors_the_reference_names() -> None:
+    """effects/registry.py:166-254,502-553 — tensor / kernel registration under the reference's class names."""
+    import torch
+
+    from spectralmc_b200.interpreter import MonteCarloInterpreter, MonteCarloOperators, SharedRegistry, TensorRegistry
+
+    assert SharedRegistry is TensorRegistry and MonteCarloInterpreter is MonteCarloOperators
+    reg = SharedRegistry()
+    assert reg.has_kernel("SimulateBlackScholes") and not reg.has_tensor("z")
+    assert isinstance(reg.register_tensor("z", torch.zeros(2, 3)), Success) and reg.has_tensor("z")
+    assert isinstance(reg.get_torch_tensor("z"), Success) and isinstance(reg.get_tensor("missing"), Failure)
+    assert isinstance(reg.register_tensor("", torch.zeros(1)), Failure)
+    assert isinstance(reg.register_kernel("mine", print), Success) and reg.get_kernel("mine").value is print
+    assert isinstance(reg.register_kernel("", print), Failure) and isinstance(reg.get_kernel("other"), Failure)
+    reg.clear_tensors()
+    assert not reg.has_tensor("z") and reg.has_kernel("mine")
