@@ -129,7 +129,7 @@ def _p2p_worker(rank: int, world: int, port: int, prec: str, queue, norm: str = 
                             device_id=torch.device("cuda", rank))
     try:
         out = {}
-        for N, B, C in ((64, 1001, 3), (48, 37, 700)):  # radix-2 and table-DFT sizes; 700 contracts > one wave of the exchange grid is not needed, but > 1 per CTA stride on small grids
+        for N, B, C in ((64, 1001, 3), (48, 37, 700), (16, 8, 3000)):  # 3000 contracts: several per CTA of the persistent exchange grid
             sp = make_simulation_params(timesteps=20, network_size=N, batches_per_mc_run=B, mc_seed=5, skip=2, dtype=Precision(prec))
             cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization(norm))
             rows = np.tile(np.asarray(ROWS), (C // 3 + 1, 1))[:C]
