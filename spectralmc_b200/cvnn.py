@@ -203,33 +203,27 @@ def describe(module: nn.Module) -> list[tuple] | None:
     return None
 
 
-class FusedCVNN:
-    """A supported network + Adam state in flat device buffers, stepped through the C ABI.
+class FlatAdam:
+    """``torch.optim.Adam`` (defaults: no weight decay, no amsgrad) over ONE flat buffer, stepped by
+    ``smc_adam_step``: the step counter lives on the device and the bias corrections are formed in float64
+    inside the kernel, so a step is capturable in a CUDA graph AND follows the eager optimiser's arithmetic
+    (torch's own capturable Adam keeps ``step`` in float32 and drifts by ~1e-7 in early steps).
 
-    Construction re-points every parameter of ``net`` at a view of one flat buffer (values
-    unchanged) and every ``.grad`` at a view of the flat gradient buffer, so the module keeps
-    working as a torch module (``state_dict``, torch ``forward``, gradient inspection); moving the
-    module afterwards (``.to()``) detaches it from the buffers and is not supported.
+    Construction re-points every parameter at a view of the flat parameter buffer (values unchanged) and
+    every ``.grad`` at a view of the flat gradient buffer; moving the module afterwards (``.to()``) detaches
+    it from the buffers and is not supported.  State is exchanged in ``torch.optim.Adam.state_dict()`` layout.
     """
 
-    def __init__(self, net: nn.Module, *, lr: float = 1e-2, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
-        layers = describe(net)
-        if not layers:
-            raise ValueError("network is not a ComplexSequential of ComplexLinear / modReLU / zReLU")
-        params = list(net.parameters())
+    def __init__(self, params: list[nn.Parameter], *, lr: float = 1e-2, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
         if not params:
-            raise ValueError("network has no parameters")
+            raise ValueError("no parameters")
+        self._params = params
         self.dtype, self.device = params[0].dtype, params[0].device
         if self.device.type != "cuda":
-            raise ValueError("FusedCVNN needs the network on a CUDA device (spectralmc_b200 has no CPU path)")
-        if layers[0][0] == "zrelu":
-            raise ValueError("cannot infer the input width of a network that starts with zReLU")
-        self.n_inputs = layers[0][1]
-        self.net, self.layers = net, layers
-        self.desc, n = _cabi.make_cvnn_net(layers, self.n_inputs, self.dtype)
-        if n != sum(p.numel() for p in params):
-            raise AssertionError("descriptor / parameter count mismatch")
-        self.n_outputs = _cabi.cvnn_output_width(self.desc)
+            raise ValueError("FlatAdam needs CUDA parameters (spectralmc_b200 has no CPU path)")
+        if any(p.dtype != self.dtype or p.device != self.device for p in params):
+            raise ValueError("parameters must share one device and dtype")
+        n = sum(p.numel() for p in params)
         self.params = torch.empty(n, dtype=self.dtype, device=self.device)
         self.grads = torch.zeros_like(self.params)
         self.exp_avg = torch.zeros_like(self.params)
@@ -246,7 +240,79 @@ class FusedCVNN:
                 p.grad = self.grads[offset : offset + k].view(p.shape)
                 self._slices.append((offset, k))
                 offset += k
+
+    def apply(self) -> None:
+        """One Adam update of the whole buffer from ``self.grads``; no host synchronisation."""
+        _cabi.adam_step(self.params, self.grads, self.exp_avg, self.exp_avg_sq, self.step, self.hyper)
+
+    def state_dict(self) -> dict:
+        step = float(self.step.item())
+        state = {}
+        if step > 0:
+            for i, (p, (o, k)) in enumerate(zip(self._params, self._slices)):
+                state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o : o + k].view(p.shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o : o + k].view(p.shape).clone()}
+        group = {"lr": self.hyper.lr, "betas": (self.hyper.beta1, self.hyper.beta2), "eps": self.hyper.eps, "weight_decay": 0,
+                 "amsgrad": False, "params": list(range(len(self._slices)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: dict) -> None:
+        group = sd["param_groups"][0]
+        self.hyper = _cabi.AdamArgs(float(group["lr"]), group["betas"][0], group["betas"][1], group["eps"])
+        steps = {float(s["step"]) for s in sd["state"].values()}
+        if len(steps) > 1:
+            raise ValueError("per-parameter step counts differ")
+        self.step.fill_(int(steps.pop()) if steps else 0)
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        for i, (o, k) in enumerate(self._slices):
+            if i in sd["state"]:
+                self.exp_avg[o : o + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o : o + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
+
+
+class FusedCVNN:
+    """A supported network + Adam state in flat device buffers (``FlatAdam``), stepped through the C ABI.
+
+    The module keeps working as a torch module (``state_dict``, torch ``forward``, gradient inspection): its
+    parameters and gradients are views of the flat buffers.
+    """
+
+    def __init__(self, net: nn.Module, *, lr: float = 1e-2, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
+        layers = describe(net)
+        if not layers:
+            raise ValueError("network is not a ComplexSequential of ComplexLinear / modReLU / zReLU")
+        params = list(net.parameters())
+        if not params:
+            raise ValueError("network has no parameters")
+        if params[0].device.type != "cuda":
+            raise ValueError("FusedCVNN needs the network on a CUDA device (spectralmc_b200 has no CPU path)")
+        if layers[0][0] == "zrelu":
+            raise ValueError("cannot infer the input width of a network that starts with zReLU")
+        self.n_inputs = layers[0][1]
+        self.net, self.layers = net, layers
+        self.adam = FlatAdam(params, lr=lr, betas=betas, eps=eps)
+        self.dtype, self.device = self.adam.dtype, self.adam.device
+        self.desc, n = _cabi.make_cvnn_net(layers, self.n_inputs, self.dtype)
+        if n != self.adam.params.numel():
+            raise AssertionError("descriptor / parameter count mismatch")
+        self.n_outputs = _cabi.cvnn_output_width(self.desc)
         self._workspaces: dict[tuple[int, bool], torch.Tensor] = {}
+
+    # the flat buffers, under the names the C ABI uses
+    params = property(lambda self: self.adam.params)
+    grads = property(lambda self: self.adam.grads)
+    exp_avg = property(lambda self: self.adam.exp_avg)
+    exp_avg_sq = property(lambda self: self.adam.exp_avg_sq)
+    step = property(lambda self: self.adam.step)
+
+    @property
+    def hyper(self) -> "_cabi.AdamArgs":
+        return self.adam.hyper
+
+    @hyper.setter
+    def hyper(self, value: "_cabi.AdamArgs") -> None:
+        self.adam.hyper = value
 
     def _workspace(self, rows: int, training: bool) -> torch.Tensor:
         key = (rows, training)
@@ -308,26 +374,7 @@ class FusedCVNN:
 
     # ---- optimiser state in torch.optim.Adam's state_dict layout (snapshot interchange) -----
     def optimizer_state_dict(self) -> dict:
-        step = float(self.step.item())
-        state = {}
-        if step > 0:
-            for i, (p, (o, k)) in enumerate(zip(self.net.parameters(), self._slices)):
-                state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o : o + k].view(p.shape).clone(),
-                            "exp_avg_sq": self.exp_avg_sq[o : o + k].view(p.shape).clone()}
-        group = {"lr": self.hyper.lr, "betas": (self.hyper.beta1, self.hyper.beta2), "eps": self.hyper.eps, "weight_decay": 0,
-                 "amsgrad": False, "params": list(range(len(self._slices)))}
-        return {"state": state, "param_groups": [group]}
+        return self.adam.state_dict()
 
     def load_optimizer_state_dict(self, sd: dict) -> None:
-        group = sd["param_groups"][0]
-        self.hyper = _cabi.AdamArgs(group["lr"], group["betas"][0], group["betas"][1], group["eps"])
-        steps = {float(s["step"]) for s in sd["state"].values()}
-        if len(steps) > 1:
-            raise ValueError("per-parameter step counts differ")
-        self.step.fill_(int(steps.pop()) if steps else 0)
-        self.exp_avg.zero_()
-        self.exp_avg_sq.zero_()
-        for i, (o, k) in enumerate(self._slices):
-            if i in sd["state"]:
-                self.exp_avg[o : o + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
-                self.exp_avg_sq[o : o + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
+        self.adam.load_state_dict(sd)

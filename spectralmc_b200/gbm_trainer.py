@@ -25,11 +25,15 @@ SURVEY.md §8f-4: when the network is a ComplexSequential of ComplexLinear / mod
 then: pinned H2D of the contracts, the simulation launches (their matrix index changes every
 step, so they stay ordinary launches), two small device copies into the graph's static inputs,
 one graph launch.  The losses stay on the device until ``train`` returns.  Any other network
-takes the generic torch route below (``fused_step=False`` forces it).
+(batch norms, residual blocks) takes the torch route (``fused_step=False`` forces it): autograd for the
+network, ``smc_adam_step`` over the flattened parameters (``FlatAdam``), captured as one CUDA graph too;
+``cuda_graph=False`` gives the reference's eager step with ``torch.optim.Adam``.  In both graphed routes the step
+runs on a high-priority second stream, one batch behind the simulation.
 """
 
 from __future__ import annotations
 
+import copy
 import math
 import time
 import warnings
@@ -41,7 +45,7 @@ import torch
 from pydantic import BaseModel, ConfigDict
 from torch import nn, optim
 
-from spectralmc_b200.cvnn import FusedCVNN, describe
+from spectralmc_b200.cvnn import FlatAdam, FusedCVNN, describe
 from spectralmc_b200.distributed import PeerExchange, sharded_cf_targets
 from spectralmc_b200.errors import (
     DeviceDTypeError,
@@ -197,6 +201,8 @@ class GbmCVNNPricer:
         self._use_graph = cuda_graph
         self._fused: FusedCVNN | None = None
         self._graphs: dict[int, _StepGraph] = {}
+        self._torch_graphs: dict[int, _TorchStepGraph] = {}  # torch route, one captured step per batch size
+        self._flat_adam: FlatAdam | None = None               # Adam of the graphed torch route (device step counter)
         self._staging: dict[tuple, list] = {}
         self._staging_next = 0
         self._nn_stream: torch.cuda.Stream | None = None  # CVNN steps run here, one step behind the simulation
@@ -277,12 +283,34 @@ class GbmCVNNPricer:
                     dict(self._optimizer_state["param_groups"][0], lr=learning_rate)]))
                 self._optimizer_state = None  # now lives in the fused buffers until the next snapshot
             return self._fused
+        if self._use_graph:
+            # graphed torch route: autograd for the network, smc_adam_step over the flattened parameters (capturable,
+            # float64 bias corrections like the eager optimiser; torch's own capturable Adam keeps `step` in float32)
+            if self._flat_adam is None:
+                self._flat_adam = FlatAdam(list(self._cvnn.parameters()), lr=learning_rate)
+            elif self._flat_adam.hyper.lr != learning_rate:
+                self._flat_adam.hyper.lr = learning_rate  # baked into the captured launch
+                self._torch_graphs.clear()
+            if self._optimizer_state is not None:
+                self._flat_adam.load_state_dict(_with_lr(self._optimizer_state, learning_rate))
+                self._optimizer_state = None
+            return self._flat_adam
         adam = optim.Adam(self._cvnn.parameters(), lr=learning_rate)
         if self._optimizer_state is not None:
-            adam.load_state_dict(self._optimizer_state)
-            for group in adam.param_groups:
-                group["lr"] = learning_rate
+            adam.load_state_dict(_with_lr(self._optimizer_state, learning_rate))
         return adam
+
+    def _torch_graph_step(self, contracts: torch.Tensor, targets: torch.Tensor, loss_slot: torch.Tensor) -> torch.Tensor:
+        """The torch route of ``_torch_step`` replayed as one CUDA graph (networks the fused step does not cover)."""
+        rows = contracts.shape[0]
+        g = self._torch_graphs.get(rows)
+        if g is None:
+            g = self._torch_graphs[rows] = _TorchStepGraph(self._cvnn, self._flat_adam, rows, contracts.shape[1], targets.shape[1], self._dtype)
+        g.real_in.copy_(contracts)
+        g.targets.copy_(targets)
+        g.graph.replay()
+        loss_slot.copy_(g.loss)
+        return g.grad_norm
 
     def train(self, config: TrainingConfig, *, logger: StepLogger | None = None) -> Result[TrainingResult, object]:
         """``config.num_batches`` optimiser steps (reference :1456-1683).  Without a ``logger`` nothing
@@ -298,7 +326,8 @@ class GbmCVNNPricer:
         # stream and overlaps the simulation of batch i + 1 — the two are independent, and the step's small
         # launches fit into the SM slots the tile kernel frees.  Same kernels in the same per-stream order, so
         # results are bit-identical to the serial schedule.
-        pipelined = self._use_fused and logger is None
+        graphed_torch = not self._use_fused and self._use_graph
+        pipelined = (self._use_fused or graphed_torch) and logger is None
         sim_stream = torch.cuda.current_stream(self._device)
         if pipelined:
             if self._nn_stream is None:
@@ -325,9 +354,14 @@ class GbmCVNNPricer:
                         self._nn_stream.wait_event(ready)
                         contracts.record_stream(self._nn_stream)  # allocated on the simulation stream, read here
                         targets.record_stream(self._nn_stream)
-                        self._fused_step(contracts, targets, losses[i : i + 1])
+                        if self._use_fused:
+                            self._fused_step(contracts, targets, losses[i : i + 1])
+                        else:
+                            grad_norm = self._torch_graph_step(contracts, targets, losses[i : i + 1])
                 elif self._use_fused:
                     self._fused_step(contracts, targets, losses[i : i + 1])
+                elif graphed_torch:
+                    grad_norm = self._torch_graph_step(contracts, targets, losses[i : i + 1])
                 else:
                     real_in = contracts.to(self._dtype)
                     loss, grad_norm = self._torch_step(real_in, torch.zeros_like(real_in), targets, optimizer)
@@ -342,7 +376,7 @@ class GbmCVNNPricer:
         if config.num_batches > 0:
             grad_norm = self._fused.grads.norm() if self._use_fused else grad_norm
         host = [float(x) for x in losses[: config.num_batches].cpu()]
-        if not self._use_fused:
+        if not self._use_fused and not self._use_graph:
             self._optimizer_state = _to_cpu(optimizer.state_dict())
         snap = self.snapshot()
         if isinstance(snap, Failure):
@@ -388,6 +422,8 @@ class GbmCVNNPricer:
         """Adam state in ``torch.optim.Adam.state_dict()`` layout (CPU) for both step routes."""
         if self._use_fused and self._fused is not None and int(self._fused.step.item()) > 0:
             return _to_cpu(self._fused.optimizer_state_dict())
+        if self._flat_adam is not None and int(self._flat_adam.step.item()) > 0:
+            return _to_cpu(self._flat_adam.state_dict())
         return self._optimizer_state
 
     def snapshot(self) -> Result[GbmCVNNPricerConfig, object]:
@@ -420,6 +456,54 @@ class _StepGraph:
         # simulation gets SM slots as soon as the big kernel frees any (see GbmCVNNPricer.train)
         with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(dev, priority=-1)):
             fused.train_step(self.real_in, self.imag_in, self.targets, self.loss)
+
+
+def _with_lr(state: dict, lr) -> dict:
+    """``state`` (Adam ``state_dict`` layout) with every group's learning rate replaced."""
+    return dict(state, param_groups=[dict(g, lr=lr) for g in state["param_groups"]])
+
+
+class _TorchStepGraph:
+    """One captured ``_torch_step`` of an arbitrary torch CVNN for a fixed batch size: forward, two MSE terms and
+    backward by torch autograd (gradients accumulate into the views of ``FlatAdam``'s zeroed gradient buffer),
+    then one ``smc_adam_step`` and the gradient norm.  cuBLAS handles and workspaces are initialised by one
+    forward/backward on a deep copy of the network, so the real parameters and statistics are untouched before
+    the capture."""
+
+    def __init__(self, net: nn.Module, adam: FlatAdam, rows: int, n_inputs: int, n_outputs: int, dtype: torch.dtype) -> None:
+        dev = adam.device
+        self.real_in = torch.zeros((rows, n_inputs), dtype=dtype, device=dev)
+        self.imag_in = torch.zeros_like(self.real_in)
+        self.targets = torch.zeros((rows, n_outputs), dtype=torch.complex64 if dtype == torch.float32 else torch.complex128, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float64, device=dev)
+        self.grad_norm = torch.zeros((), dtype=dtype, device=dev)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            twin = copy.deepcopy(net)
+            pr, pi = twin(torch.randn_like(self.real_in), self.imag_in)
+            (pr.square().mean() + pi.square().mean()).backward()
+            scratch = [torch.zeros(1, dtype=dtype, device=dev) for _ in range(4)]
+            _adam_warm_up(scratch, adam)
+            del twin, pr, pi
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(dev, priority=-1)):
+            pred_r, pred_i = net(self.real_in, self.imag_in)
+            loss = nn.functional.mse_loss(pred_r, torch.real(self.targets)) + nn.functional.mse_loss(pred_i, torch.imag(self.targets))
+            adam.grads.zero_()
+            loss.backward()
+            adam.apply()
+            self.grad_norm.copy_(adam.grads.norm())
+            self.loss.copy_(loss.detach())
+
+
+def _adam_warm_up(scratch: list[torch.Tensor], adam: FlatAdam) -> None:
+    """Load the Adam kernels outside a capture, on scratch buffers."""
+    from spectralmc_b200 import _cabi
+
+    _cabi.adam_step(scratch[0], scratch[1], scratch[2], scratch[3], torch.zeros(1, dtype=torch.int64, device=adam.device), adam.hyper)
 
 
 class _nvtx:

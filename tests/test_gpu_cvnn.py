@@ -301,13 +301,14 @@ def test_wide_network_and_large_batch() -> None:
 
 def test_factory_networks_with_batch_norm_and_residuals_train_on_the_torch_route() -> None:
     """A network using every block of the reference's factory (batch norms, residuals) is outside the
-    fused step: the trainer takes the torch route for it, deterministically."""
+    fused step: the trainer takes the torch route for it — autograd + smc_adam_step, captured once and
+    replayed as one CUDA graph — deterministically, and in step with the eager torch route."""
     from spectralmc_b200 import cvnn_factory as f
 
     def act(kind):
         return f.ActivationCfg(kind=kind)
 
-    def trainer():
+    def trainer(**kw):
         layers = [
             f.LinearCfg(width=f.ExplicitWidth(value=24), activation=act(f.ActivationKind.MOD_RELU)),
             f.CovBNCfg(),
@@ -318,7 +319,7 @@ def test_factory_networks_with_batch_norm_and_residuals_train_on_the_torch_route
         net = expect_success(f.build_model(n_inputs=6, n_outputs=16, cfg=cfg)).to("cuda", torch.float32)
         sp = make_simulation_params(timesteps=2, network_size=16, batches_per_mc_run=512, mc_seed=21, dtype=Precision.float32)
         bs = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
-        return expect_success(GbmCVNNPricer.create(expect_success(build_gbm_cvnn_pricer_config(cfg=bs, domain_bounds=make_domain_bounds(), cvnn=net))))
+        return expect_success(GbmCVNNPricer.create(expect_success(build_gbm_cvnn_pricer_config(cfg=bs, domain_bounds=make_domain_bounds(), cvnn=net)), **kw))
 
     a, b = trainer(), trainer()
     assert not a._use_fused
@@ -326,4 +327,15 @@ def test_factory_networks_with_batch_norm_and_residuals_train_on_the_torch_route
     rb = expect_success(b.train(TrainingConfig(num_batches=3, batch_size=32)))
     assert ra.losses == rb.losses and all(np.isfinite(ra.losses))
     assert all(torch.equal(x, y) for x, y in zip(_params(a), _params(b)))
+    assert len(a._torch_graphs) == 1 and a._flat_adam is not None and int(a._flat_adam.step.item()) == 3  # one captured step, replayed
+    # ... and the captured step follows the eager torch step (torch.optim.Adam, op by op) of the reference
+    c = trainer(cuda_graph=False)
+    rc = expect_success(c.train(TrainingConfig(num_batches=3, batch_size=32)))
+    assert not c._torch_graphs and max(abs(x - y) / abs(y) for x, y in zip(ra.losses, rc.losses)) <= 1e-4
+    # Adam moves a parameter whose gradient is rounding noise by +-lr per step in either direction: bound the
+    # divergence of the two float32 runs by the three steps taken, and require agreement where gradients are real
+    assert max(float((x - y).abs().max()) for x, y in zip(_params(a), _params(c))) <= 3 * 1e-2 * 1.01
+    assert nw(_params(a)[0], _params(c)[0]) <= 1e-3  # first layer's weights: large, well-defined gradients
+    sa, sc = expect_success(a.snapshot()), expect_success(c.snapshot())
+    assert set(sa.optimizer_state["state"]) == set(sc.optimizer_state["state"]) and float(sa.optimizer_state["state"][0]["step"]) == 3.0
     assert float(a._cvnn.state_dict()["layers.0.layers.1.running_C_rr"].sub(0.5).abs().max()) > 0  # statistics were tracked
