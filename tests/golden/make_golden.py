@@ -213,6 +213,19 @@ def main() -> None:
                       norm=ForwardNormalization.NORMALIZE, T=3, N=8, B=4, tpb=32, seed=9,
                       contract=dict(X0=90.0, K=100.0, T=2.0, r=0.03, d=0.01, v=0.0)))
 
+    # the headline depths: 252 steps (configs c2/c5) and 365 steps (c4) on a narrow matrix, so that the reference's
+    # own kernel body pins the error accumulation over a full-length path (the reference never tests T > 16)
+    hot = dict(X0=120.0, K=95.0, T=3.0, r=0.03, d=0.01, v=1.2)
+    cases.append(dict(name="deep_c2_float32", prec="float32", scheme=PathScheme.LOG_EULER, norm=ForwardNormalization.RAW,
+                      T=252, N=16, B=4, tpb=64, seed=7, contract=canonical))
+    cases.append(dict(name="deep_c4_float64", prec="float64", scheme=PathScheme.LOG_EULER, norm=ForwardNormalization.NORMALIZE,
+                      T=365, N=16, B=4, tpb=64, seed=31, contract=hot))
+    cases.append(dict(name="deep_simple_euler_float32", prec="float32", scheme=PathScheme.SIMPLE_EULER,
+                      norm=ForwardNormalization.NORMALIZE, T=252, N=8, B=8, tpb=32, seed=11, contract=hot))
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    if only:
+        cases = [c for c in cases if any(c["name"].startswith(o) for o in only)]
+
     for case in cases:
         recorded.clear()
         sp = ref_gbm.SimulationParams(
@@ -247,6 +260,8 @@ def main() -> None:
         )
         print(f"{case['name']:48s} cf[0]={cf[0]:.6g} dtype={cf.dtype} -> {os.path.basename(out)}")
 
+    if only:
+        return
     # Sobol contracts from the reference's own sampler (sobol_sampler.py imports cleanly)
     from spectralmc.sobol_sampler import BoundSpec, SobolConfig, SobolSampler, build_domain_bounds
 
