@@ -90,12 +90,39 @@ class PeerExchange:
             raise ValueError("the peer exchange supports at most 16 ranks")
         self.capacity_contracts, self.network_size = capacity_contracts, network_size
         nbytes = int(_cabi.LIB.smc_p2p_buffer_bytes(capacity_contracts, network_size, self.world))
-        self._own, handle = _cabi.p2p_alloc(nbytes)
+        # Set-up is collective: every rank takes part in both exchanges below even if its own allocation or
+        # mapping failed, so that a failure anywhere raises on ALL ranks instead of leaving the others blocked.
+        self._own, handle, problem = None, None, None
+        try:
+            self._own, handle = _cabi.p2p_alloc(nbytes)
+        except Exception as exc:  # noqa: BLE001 - reported to every rank below
+            problem = f"rank {self.rank}: {exc}"
         handles: list[bytes | None] = [None] * self.world
         dist.all_gather_object(handles, handle, group=group)
-        self._peers = [self._own if q == self.rank else _cabi.p2p_open(handles[q]) for q in range(self.world)]
+        self._peers: list[int] = []
+        if problem is None and all(h is not None for h in handles):
+            try:
+                self._peers = [self._own if q == self.rank else _cabi.p2p_open(handles[q]) for q in range(self.world)]
+            except Exception as exc:  # noqa: BLE001
+                problem = f"rank {self.rank}: {exc}"
+        elif problem is None:
+            problem = f"allocation failed on rank(s) {[q for q, h in enumerate(handles) if h is None]}"
+        problems: list[str | None] = [None] * self.world
+        dist.all_gather_object(problems, problem, group=group)
+        if any(p is not None for p in problems):
+            self._release()
+            raise RuntimeError("peer exchange unavailable: " + "; ".join(p for p in problems if p is not None))
         self.epoch = 0
         dist.barrier(group=group)  # every buffer is zeroed and mapped before anyone writes
+
+    def _release(self) -> None:
+        for q, ptr in enumerate(self._peers):
+            if q != self.rank:
+                _cabi.LIB.smc_p2p_close(ptr)
+        self._peers = []
+        if self._own is not None:
+            _cabi.LIB.smc_p2p_free(self._own)
+            self._own = None
 
     def next_group(self) -> "_cabi.P2PGroup":
         self.epoch += 1
@@ -110,12 +137,10 @@ class PeerExchange:
         if self._peers:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)  # nobody is still writing into a buffer that is about to go away
-            for q, ptr in enumerate(self._peers):
-                if q != self.rank:
-                    _cabi.check(_cabi.LIB.smc_p2p_close(ptr))
-            dist.barrier(group=self.group)
-            _cabi.check(_cabi.LIB.smc_p2p_free(self._own))
-            self._peers = []
+            own, self._own = self._own, None
+            self._release()                 # unmap the peers' buffers
+            dist.barrier(group=self.group)  # ... before any owner frees its own
+            _cabi.check(_cabi.LIB.smc_p2p_free(own))
 
 
 def _all_reduce_sum(t: torch.Tensor, group) -> None:

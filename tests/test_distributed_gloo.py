@@ -136,3 +136,35 @@ def test_sharded_targets_equal_the_unsharded_result(world, norm, chunk_bytes) ->
         assert np.max(np.abs(out - ref)) <= 1e-12 * np.max(np.abs(ref)), rank
         assert skip == SKIP + len(ROWS)  # every rank advances the stream by one matrix per contract
     assert np.array_equal(results[0][1], results[1][1])  # all ranks hold the same all-reduced tensor
+
+
+def _exchange_worker(rank: int, world: int, port: int, queue) -> None:
+    from spectralmc_b200.distributed import PeerExchange
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        try:
+            PeerExchange(4, 16)
+            queue.put((rank, "created"))
+        except RuntimeError as exc:
+            queue.put((rank, str(exc)))
+        dist.barrier()  # still in step with the other ranks after the failure
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_exchange_setup_fails_on_every_rank_together() -> None:
+    """Without a device every rank's exchange-buffer allocation fails; the set-up is collective, so all ranks
+    learn about it and raise (nobody is left blocked in a handle exchange), and the process group stays usable."""
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        assert results[rank].startswith("peer exchange unavailable") and "rank 0" in results[rank] and "rank 1" in results[rank]
