@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMC_VERSION 100 /* 0.1.0 */
+#define SMC_VERSION 101 /* 0.1.1 */
 
 enum smc_status {
   SMC_OK = 0,
@@ -176,10 +176,16 @@ typedef struct smc_fused_args {
 } smc_fused_args;
 
 size_t smc_cf_fused_workspace_bytes(const smc_fused_args* args);
-/* number of kernels one smc_cf_fused call launches for these arguments (for launch accounting) */
+/* number of kernels one smc_cf_fused call launches for these arguments (for launch accounting):
+ * RAW is ONE kernel (tiles, reduction tree and transform); NORMALIZE two per chunk of contracts. */
 int smc_cf_fused_launch_count(const smc_fused_args* args);
 int smc_cf_fused(const smc_fused_args* args, void* cf_out /* [n_contracts, N] complex */,
                  void* workspace, size_t workspace_bytes, void* stream);
+/* Introspection (no device access): how the simulation of `args` is cut into CTAs.
+ * out = { tiles per contract, batch rows per tile, row lanes R, reduction-tree levels, fan-in of the root };
+ * capacity >= 5.  The cut depends on the problem shape only, so results never depend on the device the job
+ * lands on. */
+int smc_cf_fused_plan(const smc_fused_args* args, int64_t* out, int capacity);
 
 size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* args);
 int smc_fused_terminal(const smc_fused_args* args, void* terminal /* [n_contracts, P_local] */,
@@ -203,8 +209,10 @@ int smc_cf_from_terminal(const smc_fused_args* args, const void* terminal,
  * 64-byte cudaIpc handle), opened by the other ranks with smc_p2p_open; all ranks must have
  * finished allocating and opening before the first call (a barrier of the caller's process group).
  * `epoch` must be > 0, equal on all ranks for one call and strictly increasing from call to call;
- * all ranks must make the same sequence of calls on one stream each.  A peer that never arrives
- * makes the kernel trap after 2^27 polls, about a minute (CUDA error at the next synchronisation, no hang).
+ * all ranks must make the same sequence of calls on one stream each.  Waiting for a peer is bounded
+ * in time (`timeout_ms`): a peer that never arrives yields NaN in the affected targets and the epoch of
+ * the call in this rank's status word (smc_p2p_status) — an error the host can report, with the CUDA
+ * context intact, instead of a device trap that would take every rank down in turn.
  */
 typedef struct smc_p2p_group {
   int rank;
@@ -213,6 +221,7 @@ typedef struct smc_p2p_group {
   int64_t capacity_contracts;  /* what the buffers were sized for (smc_p2p_buffer_bytes)        */
   int64_t network_size;
   uint32_t epoch;
+  uint32_t timeout_ms;         /* how long a kernel waits for a peer; 0 = SMC_P2P_TIMEOUT_MS or two minutes */
 } smc_p2p_group;
 
 size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world);
@@ -223,6 +232,12 @@ int smc_p2p_free(void* ptr);
 int smc_cf_fused_p2p(const smc_fused_args* args, const smc_p2p_group* group, void* cf_out,
                      void* workspace /* smc_cf_fused_workspace_bytes(args) */, size_t workspace_bytes,
                      void* stream);
+/* Every host-side check smc_cf_fused_p2p makes, without touching the device: call it BEFORE advancing
+ * the epoch, so that a failure on one rank (shape, workspace, unsupported N) cannot leave the ranks'
+ * epochs out of step. */
+int smc_cf_fused_p2p_check(const smc_fused_args* args, const smc_p2p_group* group, size_t workspace_bytes);
+/* Epoch of the first call on this rank whose wait for a peer timed out (0 = none).  Synchronises `stream`. */
+int smc_p2p_status(const smc_p2p_group* group, uint32_t* timed_out_epoch, void* stream);
 /* NORMALIZE over several GPUs on the same buffers (one epoch covers both exchanges of a step):
  *   smc_fused_terminal  ->  smc_p2p_allreduce_sum_f64(terminal_sum, n_contracts)  ->  smc_cf_from_terminal_p2p
  * smc_p2p_allreduce_sum_f64 sums `count` (<= capacity_contracts) device doubles over the ranks in place, in rank

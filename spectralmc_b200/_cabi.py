@@ -35,7 +35,7 @@ EXPORTS = (
     "smc_cvnn_workspace_bytes smc_cvnn_output_width smc_cvnn_forward smc_cvnn_loss_backward smc_adam_step "
     "smc_cvnn_train_step "
     "smc_p2p_buffer_bytes smc_p2p_alloc smc_p2p_open smc_p2p_close smc_p2p_free smc_cf_fused_p2p "
-    "smc_p2p_allreduce_sum_f64 smc_cf_from_terminal_p2p"
+    "smc_p2p_allreduce_sum_f64 smc_cf_from_terminal_p2p smc_cf_fused_p2p_check smc_p2p_status smc_cf_fused_plan"
 ).split()
 
 SMC_LAYER_LINEAR, SMC_LAYER_MODRELU, SMC_LAYER_ZRELU = 0, 1, 2
@@ -79,6 +79,7 @@ class P2PGroup(Structure):
         ("capacity_contracts", c_int64),
         ("network_size", c_int64),
         ("epoch", ctypes.c_uint32),
+        ("timeout_ms", ctypes.c_uint32),
     ]
 
 
@@ -161,6 +162,9 @@ def _load() -> ctypes.CDLL:
     lib.smc_p2p_free.argtypes = [c_void_p]
     lib.smc_cf_fused_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_p2p_allreduce_sum_f64.argtypes = [c_void_p, c_int64, POINTER(P2PGroup), c_void_p]
+    lib.smc_cf_fused_plan.argtypes = [POINTER(FusedArgs), POINTER(c_int64), c_int]
+    lib.smc_cf_fused_p2p_check.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_size_t]
+    lib.smc_p2p_status.argtypes = [POINTER(P2PGroup), POINTER(ctypes.c_uint32), c_void_p]
     lib.smc_cf_from_terminal_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_cvnn_workspace_bytes.argtypes = [POINTER(CvnnNet), c_int64, c_int]
     lib.smc_cvnn_output_width.argtypes = [POINTER(CvnnNet)]
@@ -219,6 +223,59 @@ def _require_cuda(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name} must be C-contiguous")
 
 
+def stream_handle(stream: object | None) -> int:
+    """``cudaStream_t`` (as an int) of whatever stream object the caller holds: ``None`` = torch's current
+    stream, a ``torch.cuda.Stream`` (``.cuda_stream``), a Numba stream (``.handle``, a ctypes pointer —
+    what the reference passes at gbm.py:313-314,416), a CuPy stream (``.ptr``, gbm.py:313) or a raw integer."""
+    if stream is None:
+        return _stream()
+    if isinstance(stream, int):
+        return stream
+    for attr in ("cuda_stream", "ptr", "handle"):
+        if hasattr(stream, attr):
+            h = getattr(stream, attr)
+            h = getattr(h, "value", h)  # ctypes.c_void_p -> int | None
+            return int(h) if h is not None else 0
+    raise TypeError(f"cannot take a CUDA stream handle from {type(stream).__name__}")
+
+
+_TYPESTR = {"<f4": torch.float32, "<f8": torch.float64, "=f4": torch.float32, "=f8": torch.float64}
+
+
+def device_matrix(obj: object, name: str = "io") -> tuple[int, tuple[int, ...], torch.dtype, object]:
+    """(device pointer, shape, dtype, keep-alive) of a C-contiguous float32/float64 device array given as a
+    torch tensor, any object with ``__cuda_array_interface__`` (Numba device arrays — the reference passes
+    ``cuda.as_cuda_array(sims)``, gbm.py:418 — and CuPy arrays) or a DLPack exporter.  Zero-copy in every case."""
+    if isinstance(obj, torch.Tensor):
+        _require_cuda(obj, name)
+        dtype_code(obj.dtype)
+        return obj.data_ptr(), tuple(obj.shape), obj.dtype, obj
+    cai = getattr(obj, "__cuda_array_interface__", None)
+    if cai is not None:
+        shape = tuple(int(x) for x in cai["shape"])
+        dtype = _TYPESTR.get(cai["typestr"])
+        if dtype is None:
+            raise TypeError(f"{name}: unsupported element type {cai['typestr']} (float32 / float64 only)")
+        ptr, readonly = cai["data"]
+        if readonly:
+            raise ValueError(f"{name}: the device array is read-only")
+        strides = cai.get("strides")
+        if strides is not None:
+            expect, acc = [], dtype.itemsize
+            for dim in reversed(shape):
+                expect.append(acc)
+                acc *= dim
+            if tuple(strides) != tuple(reversed(expect)):
+                raise ValueError(f"{name} must be C-contiguous")
+        if ptr is None or (ptr == 0 and all(shape)):
+            raise ValueError(f"{name}: NULL device pointer")
+        return int(ptr), shape, dtype, obj
+    if hasattr(obj, "__dlpack__"):
+        t = torch.from_dlpack(obj)
+        return device_matrix(t, name)[:3] + (t,)
+    raise TypeError(f"{name} must be a CUDA tensor or expose __cuda_array_interface__ / __dlpack__; got {type(obj).__name__}")
+
+
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
@@ -233,14 +290,17 @@ def philox_normals(out: torch.Tensor, seed: int, matrix_index: int) -> torch.Ten
 
 
 def gbm_paths_inplace(
-    io: torch.Tensor, dt: float, X0: float, r: float, d: float, v: float, scheme: int, threads_per_block: int = 256
+    io: object, dt: float, X0: float, r: float, d: float, v: float, scheme: int, threads_per_block: int = 256,
+    stream: object | None = None,
 ) -> None:
-    """K2: the reference's ``SimulateBlackScholes`` launch on a materialised matrix."""
-    _require_cuda(io, "io")
-    rows, cols = io.shape
+    """K2: the reference's ``SimulateBlackScholes`` launch on a materialised matrix.  ``io`` is any device
+    array ``device_matrix`` accepts; ``stream`` anything ``stream_handle`` accepts (default: torch's current)."""
+    ptr, shape, dtype, _keep = device_matrix(io, "io")
+    if len(shape) != 2:
+        raise ValueError(f"io must be a (timesteps, paths) matrix; got shape {shape}")
     check(
         LIB.smc_gbm_paths_inplace(
-            io.data_ptr(), rows, cols, dtype_code(io.dtype), dt, X0, r, d, v, scheme, threads_per_block, _stream()
+            ptr, shape[0], shape[1], dtype_code(dtype), dt, X0, r, d, v, scheme, threads_per_block, stream_handle(stream)
         )
     )
 
@@ -393,6 +453,13 @@ def cf_fused_host(args: FusedArgs, contracts_host: torch.Tensor, out_host: torch
             byref(args), contracts_host.data_ptr(), out_host.data_ptr(), workspace.data_ptr(), workspace.numel(), _stream()
         )
     )
+
+
+def cf_fused_plan(args: FusedArgs) -> dict:
+    """How the simulation of ``args`` is cut into CTAs (``smc_cf_fused_plan``; no device access)."""
+    out = (c_int64 * 8)()
+    check(LIB.smc_cf_fused_plan(byref(args), out, 8))
+    return {"tiles": int(out[0]), "tile_rows": int(out[1]), "row_lanes": int(out[2]), "levels": int(out[3]), "root_fan_in": int(out[4])}
 
 
 def cf_fused_host_workspace_bytes(args: FusedArgs) -> int:

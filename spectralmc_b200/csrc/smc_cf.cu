@@ -1,5 +1,5 @@
 // Fused batch path and CF estimate: in-register Philox normals -> GBM stepping -> payoff ->
-// column sums over batches -> one FFT per contract.
+// column sums over batches -> one FFT per contract, as ONE persistent kernel per step.
 //
 // Replaces, per training step, the reference's Python loop
 //   [ _simulate_fft(c) for c in sobol_inputs ] + cp.asarray(fft_values)
@@ -8,21 +8,31 @@
 // and, for materialised inputs, cp.mean(cp.fft.fft(mat, axis=1), axis=0) (gbm_trainer.py:814-817).
 //
 // Structure (all reductions fixed-order, no float atomics => bit-reproducible):
-//   tile_kernel      one CTA per (contract, tile of batch rows).  Thread (r, col) owns column
-//                    `col` of the [B, N] payoff matrix and walks rows r, r+R, ... of its tile,
+//   step_kernel      a persistent grid of co-resident CTAs (occupancy x SM count) draws work items
+//                    (contract, tile of batch rows) from a device counter.  Thread (r, col) owns
+//                    column `col` of the [B, N] payoff matrix and walks rows r, r+R, ... of its tile,
 //                    accumulating in float64; the CTA folds the R row-lanes in shared memory and
 //                    writes one partial column-sum vector per tile.
-//   reduce_tiles     folds the tile partials of a contract into <= 64 group vectors.
-//   cf_finalize      folds the groups, scales by 1/B and takes ONE length-N transform
-//                    (mean_b FFT_n(mat) == FFT_n(mean_b mat)) in float64 shared memory
-//                    (radix-2 for powers of two, table-driven DFT otherwise), then narrows to
-//                    the output complex width.
-// The tile size is a function of the problem shape only (never of the SM count), so results do
-// not depend on the device the job lands on.
+//   ticket tree      the tile vectors of a contract are the leaves of a radix-16 tree.  A CTA that
+//                    completes a vector takes a ticket (atomic counter) on its parent; whoever takes
+//                    the LAST ticket of a node folds that node's children in index order (so the sum
+//                    never depends on which CTA, or how many SMs, did the work) and moves up.
+//   finish_contract  the CTA that completes the root scales by 1/B and takes ONE length-N transform
+//                    (mean_b FFT_n(mat) == FFT_n(mean_b mat)) in float64 shared memory (radix-2 for
+//                    powers of two, table-driven DFT otherwise) and narrows to the output width —
+//                    or, for batch-sharded multi-GPU runs, pushes the real vector into every peer's
+//                    exchange buffer; a second phase of the same kernel sums the peers' vectors.
+//   Large N (transform working set > 16 KiB of shared memory) keeps the transform in a separate
+//   one-CTA-per-contract kernel (cf_finalize_kernel / cf_exchange_finalize_kernel).
+// Tile and tree shapes are functions of the problem shape only (never of the SM count), and a
+// tile's vector does not depend on which CTA computed it, so results do not depend on the device
+// the job lands on or on the dynamic schedule.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "smc_device.cuh"
 #include "smc_internal.h"
@@ -32,46 +42,104 @@ namespace smc {
 constexpr int CF_BLOCK = 256;
 constexpr int64_t TARGET_TILES = 16384;
 constexpr int64_t STREAM_TILES = 2368;  // 16 x 148
-constexpr int MAX_GROUPS = 64;
+constexpr int64_t MIN_TILE_PATH_STEPS = 16384;  // a simulated tile is at least 64 path-steps per thread
+constexpr int TREE_RADIX = 16;
+constexpr int MAX_LEVELS = 8;           // 16^8 > 2^31 tiles
+constexpr size_t FUSED_FINALIZE_SMEM_MAX = 16 * 1024;  // transform working set that may live in the step kernel
 constexpr int SCHEME_LOG_STEPWISE = 2;  // SMC_LOG_EULER_STEPWISE
+constexpr int MAX_PEERS = 16;
+
+#ifndef SMC_TAIL_NOINLINE
+#define SMC_TAIL_NOINLINE 1  // codegen knob: the cold per-tile tail (tickets, folds, transform) as out-of-line functions
+#endif
+#if SMC_TAIL_NOINLINE
+#define SMC_COLD __noinline__
+#else
+#define SMC_COLD __forceinline__
+#endif
 
 enum Source { SRC_FUSED = 0, SRC_TERMINAL = 1, SRC_MATRIX = 2 };
 enum Output { OUT_COLSUM = 0, OUT_TERMINAL = 1 };
+enum Finish { FINISH_NONE = 0, FINISH_TRANSFORM = 1, FINISH_EXCHANGE = 2 };
+
+// Radix-16 reduction tree over the tile vectors of ONE contract.  Level 0 are the tiles; level l has
+// count[l] = ceil(count[l-1] / 16) nodes; the root folds the count[levels] <= 16 vectors of the top level.
+struct TreePlan {
+  int levels;                     // intermediate levels (0 when tiles <= 16)
+  int64_t count[MAX_LEVELS + 1];
+  int64_t off[MAX_LEVELS + 1];    // first node of level l >= 1 within a contract's node storage
+  int64_t nodes;                  // intermediate nodes per contract
+};
+
+static TreePlan make_tree(int64_t tiles) {
+  TreePlan t{};
+  t.count[0] = tiles;
+  while (t.count[t.levels] > TREE_RADIX && t.levels < MAX_LEVELS) {
+    const int l = t.levels + 1;
+    t.count[l] = (t.count[l - 1] + TREE_RADIX - 1) / TREE_RADIX;
+    t.off[l] = t.nodes;
+    t.nodes += t.count[l];
+    t.levels = l;
+  }
+  return t;
+}
 
 struct TilePlan {
   int chunk_w;          // columns covered per pass (min(N, 256))
   int lanes_r;          // R: row lanes per pass (256 / chunk_w)
   int64_t tile_rows;    // multiple of R
   int64_t tiles;        // tiles per contract
-  int64_t groups;       // level-1 groups per contract (<= 64)
-  int64_t tiles_per_group;
+  TreePlan tree;
 };
+
+static int64_t env_int(const char* name, int64_t fallback) {
+  const char* e = std::getenv(name);
+  const long long v = e ? std::atoll(e) : 0;
+  return v > 0 ? static_cast<int64_t>(v) : fallback;
+}
 
 // `streaming`: the tile's source is an HBM-resident matrix (payoffs / staged terminals), so tiles
 // are sized for bandwidth (>= 64 KiB of input each, a few thousand CTAs) instead of for
-// load-balancing a compute-bound simulation.
-static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n, bool streaming = false) {
-  TilePlan p;
+// load-balancing a compute-bound simulation.  Simulated tiles (`timesteps` > 0) are sized for about
+// TARGET_TILES CTAs per launch but never below MIN_TILE_PATH_STEPS path-steps, so that short paths
+// (the reference's own tests run one timestep) do not drown in per-tile bookkeeping.
+// One tile = one CTA, handed out by the hardware block scheduler.  (A persistent grid drawing tiles
+// from a device counter was measured and rejected: the warp scheduler is not fair between resident
+// CTAs — in one 1.4 ms launch some CTAs completed 53 tiles and others 4 — so the last tiles of starved
+// CTAs stretched the tail by 100-400 us; freshly launched CTAs rotate through the priorities instead.
+// profiles/r2_persistent_grid_experiment.md.)
+static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n, bool streaming = false,
+                          int64_t timesteps = 0) {
+  TilePlan p{};
   p.chunk_w = static_cast<int>(std::min<int64_t>(n, CF_BLOCK));
   p.lanes_r = CF_BLOCK / p.chunk_w;
   const int64_t R = p.lanes_r;
-  static const int64_t target_tiles = [] {  // tuning knob: SMC_TARGET_TILES overrides the default
-    const char* e = std::getenv("SMC_TARGET_TILES");
-    const long long v = e ? std::atoll(e) : 0;
-    return v > 0 ? static_cast<int64_t>(v) : TARGET_TILES;
-  }();
+  static const int64_t target_tiles = env_int("SMC_TARGET_TILES", TARGET_TILES);  // tuning knob
   const int64_t target = streaming ? STREAM_TILES : target_tiles;
   int64_t want = (n_contracts * rows_local + target - 1) / target;
   if (streaming) want = std::max<int64_t>(want, (16384 + n - 1) / n);  // >= 16 Ki elements per tile
+  if (!streaming && timesteps > 0) {
+    const int64_t per_row = n * timesteps;
+    want = std::max<int64_t>(want, (MIN_TILE_PATH_STEPS + per_row - 1) / per_row);
+  }
   want = std::max<int64_t>(want, 1);
   p.tile_rows = (want + R - 1) / R * R;
   p.tile_rows = std::min<int64_t>(p.tile_rows, (rows_local + R - 1) / R * R);
   p.tiles = (rows_local + p.tile_rows - 1) / p.tile_rows;
-  p.tiles_per_group = (p.tiles + MAX_GROUPS - 1) / MAX_GROUPS;
-  p.groups = (p.tiles + p.tiles_per_group - 1) / p.tiles_per_group;
+  p.tree = make_tree(p.tiles);
   return p;
 }
 
+// Exchange buffers of the peer-memory all-reduce (see the section further down).
+struct PeerExchange {
+  double* data[MAX_PEERS];     // exchange buffer of rank p as mapped into this process
+  int rank, world;
+  unsigned epoch;              // > 0, the same on every rank for one call, increasing
+  int64_t capacity_contracts;  // contracts the buffers were sized for
+  unsigned long long timeout_ns;  // a peer that does not arrive within this time is reported, not waited for
+};
+
+// Everything one launch of the step kernel needs (passed by value: constant bank).
 struct TileParams {
   const double* contracts;      // [*, 6], indexed by GLOBAL contract
   int64_t contract0;            // first global contract handled by this launch
@@ -83,8 +151,8 @@ struct TileParams {
   int64_t tile_rows, tiles;
   int chunk_w, lanes_r;
   int chunk_shift;              // log2(chunk_w) when it is a power of two, else -1
+  int scheme;
   int64_t launch_contracts;     // contracts covered by this launch
-  const void* consts;           // SimConsts<Real>[launch contracts], written by prep_consts_kernel
   int normalize;                // apply scale[c] = F / mean before the payoff
   PhiloxKeys keys;
   uint64_t first_matrix_index;
@@ -94,6 +162,21 @@ struct TileParams {
   void* terminal_out;           // [launch contracts, paths_local]   (OUT_TERMINAL)
   double* partial;              // [launch contracts, tiles, n]      (OUT_COLSUM)
   double* term_partial;         // [launch contracts, tiles]         (OUT_TERMINAL)
+  double* terminal_sum_out;     // [launch contracts]                (OUT_TERMINAL): local sums
+  // per-contract constants: computed by the first CTAs that need them, then shared through this table
+  void* consts;                 // SimConsts<Real>[launch contracts]
+  unsigned* consts_ready;       // [launch contracts], zeroed before the launch
+  // reduction tree
+  unsigned* tickets;            // OUT_COLSUM: [launch contracts, tree.nodes + 1]; OUT_TERMINAL: [launch contracts]
+  double* nodes;                // [launch contracts, tree.nodes, n]
+  TreePlan tree;
+  // what the CTA that completes a contract's root does
+  int finish;                   // Finish
+  int fft_mode, log2n;          // see transform_store
+  double scale;                 // 1 / batches_total
+  void* out;                    // [*, n] complex
+  int64_t out_contract0;
+  PeerExchange px;              // FINISH_EXCHANGE
 };
 
 // per-contract constants, derived in float64 and narrowed once
@@ -106,7 +189,7 @@ struct SimConsts {
 };
 
 template <typename Real>
-__device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int SCHEME, int64_t c_global,
+__device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, const int SCHEME, int64_t c_global,
                                                        int64_t c_local) {
   const ContractRow k = load_contract(p.contracts, c_global);
   const double dt = k.T / static_cast<double>(p.timesteps);  // gbm.py:411
@@ -140,13 +223,41 @@ __device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, int 
   return s;
 }
 
-// Per-contract constants are formed ONCE per launch sequence by this small kernel (float64
-// exp/sqrt/divide), so the hot kernel's CTAs start with a handful of loads instead of competing
-// for the FP64 and XU pipes in every prologue.
+// Per-contract constants (float64 exp/sqrt/divide, out of line so the hot kernel's register allocation
+// does not see them) are formed by whichever CTAs reach a contract first and shared with every later
+// CTA through a table in the workspace: `ready[c]` (zeroed before the launch) is set with release
+// semantics once table[c] is written.  A thread that finds the flag clear does not wait — it computes
+// the same values itself — so nothing depends on the order in which CTAs are scheduled, and neither route
+// contains a barrier (threads of one CTA may see different flag values).
 template <typename Real>
-__global__ void __launch_bounds__(CF_BLOCK) prep_consts_kernel(const TileParams p, int scheme, SimConsts<Real>* out) {
-  const int64_t c_local = static_cast<int64_t>(blockIdx.x) * CF_BLOCK + threadIdx.x;
-  if (c_local < p.launch_contracts) out[c_local] = make_consts<Real>(p, scheme, p.contract0 + c_local, c_local);
+static __device__ __noinline__ void compute_consts(const TileParams& p, int64_t c_local, SimConsts<Real>* out) {
+  *out = make_consts<Real>(p, p.scheme, p.contract0 + c_local, c_local);
+}
+
+__device__ __forceinline__ unsigned load_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void store_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <typename Real>
+__device__ __forceinline__ SimConsts<Real> contract_consts(const TileParams& p, int64_t c_local) {
+  Real* table = reinterpret_cast<Real*>(static_cast<SimConsts<Real>*>(p.consts) + c_local);
+  SimConsts<Real> k;
+  if (load_acquire_gpu(p.consts_ready + c_local) != 0u) {
+    k.X0 = __ldcg(table + 0); k.K = __ldcg(table + 1); k.df = __ldcg(table + 2); k.scale = __ldcg(table + 3);
+    k.lin0 = __ldcg(table + 4); k.lin1 = __ldcg(table + 5);
+  } else {
+    compute_consts<Real>(p, c_local, &k);
+    if (threadIdx.x == 0) {
+      table[0] = k.X0; table[1] = k.K; table[2] = k.df; table[3] = k.scale; table[4] = k.lin0; table[5] = k.lin1;
+      store_release_gpu(p.consts_ready + c_local, 1u);
+    }
+  }
+  return k;
 }
 
 template <typename Real, int SCHEME>
@@ -176,7 +287,7 @@ __device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>
 // on ptxas' interleaving of IMAD.WIDE / MUFU / LOP3 issue, and merely compiling the tail code into
 // the same kernel costs 2 % at config c2 (A/B in one run: 1.387 vs 1.414 ms), so kernels that
 // cannot have a tail do not contain one.
-template <int SCHEME, bool REFINE, bool RAGGED>
+template <int SCHEME, bool REFINE, bool RAGGED, bool RAWSUM = false>
 __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi,
                                                    uint32_t& min_word) {
@@ -229,8 +340,8 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
         if (u < rem) consume<float, SCHEME>(acc, z[u], k);
     }
   }
-  if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
-  return acc;
+  if (SCHEME == SMC_LOG_EULER && !RAWSUM) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
+  return acc;  // RAWSUM: the sum of the path's normals; the caller applies X0 * 2^(lin0 + lin1 * sum)
 }
 
 // the rare re-simulation (some block of the path had a zero radius field): same path with the
@@ -270,6 +381,34 @@ __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, ui
 #endif
 }
 
+// Log-Euler float32 only: the SUM of the path's normals, with no per-contract constant in sight, so
+// that the hot loop keeps no constant live in a register; the caller reads X0 / lin0 / lin1 from shared
+// memory afterwards (SMC_CONSTS_LATE).
+template <bool RAGGED>
+static __device__ __noinline__ float simulate_logsum_exact_f32(uint32_t col, int64_t timesteps, uint32_t seed_lo, uint32_t seed_hi,
+                                                              uint32_t k_lo, uint32_t k_hi) {
+  PhiloxKeys keys;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    keys.k0[r] = seed_lo + static_cast<uint32_t>(r) * PHILOX_W0;
+    keys.k1[r] = seed_hi + static_cast<uint32_t>(r) * PHILOX_W1;
+  }
+  const SimConsts<float> none{};
+  uint32_t unused = 0;
+  return simulate_path_f32<SMC_LOG_EULER, true, RAGGED, true>(none, col, timesteps, keys, k_lo, k_hi, unused);
+}
+
+template <bool RAGGED>
+__device__ __forceinline__ float simulate_logsum_f32(uint32_t col, int64_t timesteps, const PhiloxKeys& keys, uint32_t k_lo,
+                                                     uint32_t k_hi) {
+  uint32_t min_word = 0xffffffffu;
+  const SimConsts<float> none{};
+  float s = simulate_path_f32<SMC_LOG_EULER, false, RAGGED, true>(none, col, timesteps, keys, k_lo, k_hi, min_word);
+  if (__builtin_expect(min_word < 2048u, 0))
+    s = simulate_logsum_exact_f32<RAGGED>(col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
+  return s;
+}
+
 template <int SCHEME, bool RAGGED>
 __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, uint32_t col, int64_t timesteps,
                                                     const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
@@ -297,146 +436,6 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
   }
   if (SCHEME == SMC_LOG_EULER) return k.X0 * exp(fma(k.lin1, acc, k.lin0));
   return acc;
-}
-
-#ifndef SMC_F64_FUSED_MIN_CTAS
-#define SMC_F64_FUSED_MIN_CTAS 4
-#endif
-#ifndef SMC_F32_FUSED_MIN_CTAS_OTHER
-#define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
-#endif
-#ifndef SMC_F32_FUSED_MIN_CTAS_TERMINAL
-#define SMC_F32_FUSED_MIN_CTAS_TERMINAL 4  // log-Euler with staged terminals (NORMALIZE pass A): 1.360 ms at c2 vs 1.445 at 5
-#endif
-#ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 5  // with SMC_F32X2=1: measured best (1.322 ms vs 1.385 at 4, 1.341 at 6; profiles/r1_codegen_variant_matrix.txt)
-#endif
-// float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
-// registers and run 2 CTAs per SM
-template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
-__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER)))
-    tile_kernel(const TileParams p) {
-  __shared__ double sm[CF_BLOCK];
-  const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
-  if (c_local >= p.launch_contracts) return;
-  const int64_t tile = blockIdx.x;
-  const int64_t c_global = p.contract0 + c_local;
-  const int64_t row0 = p.row_begin + tile * p.tile_rows;
-  const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
-
-  SimConsts<Real> k{};
-  if (SRC != SRC_MATRIX) {
-    const Real* kc = reinterpret_cast<const Real*>(static_cast<const SimConsts<Real>*>(p.consts) + c_local);
-    k.X0 = __ldg(kc + 0); k.K = __ldg(kc + 1); k.df = __ldg(kc + 2); k.scale = __ldg(kc + 3);
-    k.lin0 = __ldg(kc + 4); k.lin1 = __ldg(kc + 5);
-  }
-  const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
-  const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
-
-  const int r = p.chunk_shift >= 0 ? static_cast<int>(threadIdx.x >> p.chunk_shift) : static_cast<int>(threadIdx.x) / p.chunk_w;
-  const int lc = threadIdx.x - r * p.chunk_w;
-  const int64_t local_base = c_local * p.paths_local - p.row_begin * p.n;  // + global path -> staging index
-  double tile_total = 0.0;
-
-  for (int64_t n0 = 0; n0 < p.n; n0 += p.chunk_w) {
-    const int64_t col = n0 + lc;
-    const bool active = (r < p.lanes_r) && (col < p.n);
-    double acc = 0.0;
-    if (active) {
-      for (int64_t row = row0 + r; row < row1; row += p.lanes_r) {
-        const int64_t path = row * p.n + col;  // global path index b*N + n (gbm_trainer.py:814-816)
-        Real val;
-        if (SRC == SRC_FUSED)
-          val = simulate_terminal<SCHEME, RAGGED>(k, static_cast<uint32_t>(path), p.timesteps, p.keys, k_lo, k_hi);
-        else if (SRC == SRC_TERMINAL)
-          val = __ldcs(static_cast<const Real*>(p.terminal_in) + local_base + path);
-        else
-          val = __ldcs(static_cast<const Real*>(p.matrix) + (path - p.row_begin * p.n));
-        if (OUT == OUT_TERMINAL) {
-          static_cast<Real*>(p.terminal_out)[local_base + path] = val;
-          acc += static_cast<double>(val);
-        } else if (SRC == SRC_MATRIX) {
-          acc += static_cast<double>(val);
-        } else {
-          if (p.normalize) val *= k.scale;                              // gbm.py:438
-          const Real diff = k.K - val;
-          const Real put = k.df * (diff > Real(0) ? diff : Real(0));    // gbm.py:473
-          acc += static_cast<double>(put);
-        }
-      }
-    }
-    if (OUT == OUT_COLSUM) {
-      sm[threadIdx.x] = acc;
-      __syncthreads();
-      if (r == 0 && col < p.n) {
-        double s = 0.0;
-        for (int rr = 0; rr < p.lanes_r; ++rr) s += sm[rr * p.chunk_w + lc];
-        p.partial[(c_local * p.tiles + tile) * p.n + col] = s;
-      }
-      __syncthreads();
-    } else {
-      tile_total += acc;
-    }
-  }
-  if (OUT == OUT_TERMINAL) {
-    const double t = block_sum(tile_total, sm);
-    if (threadIdx.x == 0) p.term_partial[c_local * p.tiles + tile] = t;
-  }
-}
-
-// s += v[0] + v[stride] + ... (count terms), in index order, with eight loads in flight: these
-// second-level reductions read L2-resident partials and are bound by load latency, not bandwidth.
-__device__ __forceinline__ double strided_sum(const double* __restrict__ v, int64_t count, int64_t stride) {
-  double s = 0.0;
-  int64_t i = 0;
-  for (; i + 8 <= count; i += 8) {
-    double x[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) x[u] = v[(i + u) * stride];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s += x[u];
-  }
-  for (; i < count; ++i) s += v[i * stride];
-  return s;
-}
-
-// level 1: groups of tile partials -> [contracts, groups, n].  When n <= 128 the CTA's 256 threads
-// split into `subs` lanes per column, each summing every subs-th tile of the group; the lanes are
-// folded in shared memory in a fixed order.
-__global__ void __launch_bounds__(CF_BLOCK)
-    reduce_tiles_kernel(const double* __restrict__ partial, double* __restrict__ grouped, int64_t tiles,
-                        int64_t tiles_per_group, int64_t groups, int64_t n, int subs) {
-  __shared__ double sm[CF_BLOCK];
-  const int64_t c = blockIdx.x / groups, g = blockIdx.x - c * groups;
-  const int64_t t0 = g * tiles_per_group, t1 = min(t0 + tiles_per_group, tiles);
-  const double* src = partial + c * tiles * n;
-  if (subs > 1) {  // n * subs == CF_BLOCK
-    const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
-    const int64_t mine = t0 + sub < t1 ? (t1 - t0 - sub + subs - 1) / subs : 0;  // tiles t0 + sub, t0 + sub + subs, ...
-    const double s = strided_sum(src + (t0 + sub) * n + col, mine, static_cast<int64_t>(subs) * n);
-    sm[threadIdx.x] = s;
-    __syncthreads();
-    if (sub == 0) {
-      double tot = 0.0;
-      for (int k = 0; k < subs; ++k) tot += sm[k * n + col];
-      grouped[(c * groups + g) * n + col] = tot;
-    }
-    return;
-  }
-  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK)
-    grouped[(c * groups + g) * n + col] = strided_sum(src + t0 * n + col, t1 - t0, n);
-}
-
-// sum of a contract's per-tile terminal sums (fixed order)
-__global__ void __launch_bounds__(CF_BLOCK)
-    terminal_sum_kernel(const double* __restrict__ term_partial, double* __restrict__ out, int64_t tiles) {
-  __shared__ double sm[32];
-  const int64_t c = blockIdx.x;
-  double s = 0.0;
-  if (threadIdx.x < tiles)  // this thread's tiles: threadIdx.x, threadIdx.x + 256, ... (eight loads in flight)
-    s = strided_sum(term_partial + c * tiles + threadIdx.x, (tiles - threadIdx.x + CF_BLOCK - 1) / CF_BLOCK, CF_BLOCK);
-  const double tot = block_sum(s, sm);
-  if (threadIdx.x == 0) out[c] = tot;
 }
 
 __device__ __forceinline__ unsigned bit_reverse(unsigned x, int bits) { return __brev(x) >> (32 - bits); }
@@ -494,18 +493,339 @@ __device__ __forceinline__ void transform_store(double* re, double* im, const do
   }
 }
 
-// One CTA per contract: fold `groups` vectors, scale, transform, narrow.
+// s += v[0] + v[stride] + ... (count terms), in index order, with eight loads in flight: these
+// second-level reductions read L2-resident vectors written by other CTAs (hence the L2-only loads)
+// and are bound by load latency, not bandwidth.
+__device__ __forceinline__ double strided_sum(const double* __restrict__ v, int64_t count, int64_t stride) {
+  double s = 0.0;
+  int64_t i = 0;
+  for (; i + 8 <= count; i += 8) {
+    double x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = __ldcg(v + (i + u) * stride);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u];
+  }
+  for (; i < count; ++i) s += __ldcg(v + i * stride);
+  return s;
+}
+
+// Column-wise sum of `count` length-n vectors (src, src + n, ...), in a fixed order, by the whole CTA;
+// emit(col, sum) is called once per column by one thread.  When n divides 128 the CTA's 256 threads
+// split into `subs` lanes per column, each summing every subs-th vector; the lanes are folded in
+// shared memory in lane order.  `sm` holds CF_BLOCK doubles and is free again on return.
+template <typename Emit>
+__device__ __forceinline__ void fold_vectors(const double* __restrict__ src, int64_t count, int64_t n, double* sm,
+                                             Emit emit) {
+  if (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) {
+    const int subs = CF_BLOCK / static_cast<int>(n);
+    const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
+    const int64_t mine = sub < count ? (count - sub + subs - 1) / subs : 0;  // vectors sub, sub + subs, ...
+    sm[threadIdx.x] = strided_sum(src + static_cast<int64_t>(sub) * n + col, mine, static_cast<int64_t>(subs) * n);
+    __syncthreads();
+    if (sub == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < subs; ++k) tot += sm[k * n + col];
+      emit(static_cast<int64_t>(col), tot);
+    }
+    __syncthreads();
+    return;
+  }
+  for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) emit(col, strided_sum(src + col, count, n));
+}
+
+__device__ __forceinline__ void store_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned load_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Exchange buffer of one rank, in 8-byte cells:
+//   [2 slots][world senders][capacity contracts][n]   partial column sums          (exchange-finalise)
+//   [2 slots][world senders][capacity contracts]      their per-contract flags
+//   [2 slots][world senders][capacity contracts]      one double per contract      (small all-reduce: terminal sums)
+//   [2 slots][world senders]                          its per-sender flags
+//   [1]                                               status: epoch of the first call that timed out waiting for a peer
+__host__ __device__ inline size_t exchange_data_doubles(int64_t capacity_contracts, int64_t n, int world) {
+  return static_cast<size_t>(2) * world * capacity_contracts * n;
+}
+__host__ __device__ inline size_t exchange_small_base(int64_t capacity_contracts, int64_t n, int world) {
+  return exchange_data_doubles(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts;
+}
+__host__ __device__ inline size_t exchange_status_cell(int64_t capacity_contracts, int64_t n, int world) {
+  return exchange_small_base(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts +
+         static_cast<size_t>(2) * world;
+}
+__host__ __device__ inline size_t exchange_total_cells(int64_t capacity_contracts, int64_t n, int world) {
+  return exchange_status_cell(capacity_contracts, n, world) + 1;
+}
+
+// Wait until `flag` (in this rank's own exchange buffer) carries `epoch`.  Returns false when the peer
+// did not arrive within px.timeout_ns: the caller then poisons its output with NaN and the epoch is
+// recorded in the buffer's status cell (smc_p2p_status) — a reportable error instead of a trap that
+// would kill the context of every rank in turn.
+__device__ __forceinline__ bool wait_for_flag(const unsigned* flag, const PeerExchange& px, size_t status_cell) {
+  if (load_acquire_sys(flag) == px.epoch) return true;
+  const unsigned long long t0 = global_timer_ns();
+  for (unsigned polls = 1;; ++polls) {
+    if (load_acquire_sys(flag) == px.epoch) return true;
+    if ((polls & 1023u) == 0u && global_timer_ns() - t0 > px.timeout_ns) {
+      atomicCAS(reinterpret_cast<unsigned*>(px.data[px.rank] + status_cell), 0u, px.epoch);
+      return false;
+    }
+  }
+}
+
+// ---- what the CTA holding the last ticket of a contract does ---------------------------------
+// Shared memory (doubles) behind `dyn`: re[n], im[n], then the twiddle table (n/2 pairs for radix-2,
+// n pairs for the table DFT).
+template <typename Real>
+static __device__ SMC_COLD void finish_contract(const TileParams& p, int64_t c_local, const double* top,
+                                                    int64_t top_count, double* sm, double* dyn) {
+  const int64_t n = p.n;
+  if (p.finish == FINISH_TRANSFORM) {
+    double* re = dyn;
+    double* im = dyn + n;
+    double* twr = dyn + 2 * n;
+    double* twi = twr + (p.fft_mode == 0 ? n / 2 : n);
+    fill_twiddles(twr, twi, p.fft_mode == 0 ? n / 2 : n, n);
+    fold_vectors(top, top_count, n, sm, [&](int64_t col, double v) {
+      int64_t where = col;
+      if (p.fft_mode == 0 && p.log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), p.log2n));
+      re[where] = v * p.scale;
+      im[where] = 0.0;
+    });
+    __syncthreads();
+    transform_store<Real>(re, im, twr, twi, n, p.fft_mode, static_cast<Real*>(p.out) + (p.out_contract0 + c_local) * n * 2);
+    __syncthreads();  // re / im may be reused by this CTA's next contract
+  } else if (p.finish == FINISH_EXCHANGE) {
+    // phase 1 of the peer exchange: store the scaled real vector into every peer's buffer, then publish
+    const PeerExchange& px = p.px;
+    const size_t cell = ((static_cast<size_t>(px.epoch & 1u) * px.world + px.rank) * px.capacity_contracts + c_local);
+    fold_vectors(top, top_count, n, sm, [&](int64_t col, double v) {
+      const double x = v * p.scale;
+      for (int q = 0; q < px.world; ++q) px.data[q][cell * n + col] = x;
+    });
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < px.world)
+      store_release_sys(reinterpret_cast<unsigned*>(px.data[threadIdx.x] + exchange_data_doubles(px.capacity_contracts, n, px.world) + cell),
+                        px.epoch);
+  }
+  // FINISH_NONE: the top-level vectors stay where they are for a separate finalise kernel
+}
+
+// Called by every thread of a CTA after it has written tile vector `tile` of contract `c_local`:
+// walks up the ticket tree for as long as this CTA completes nodes.
+template <typename Real>
+static __device__ SMC_COLD void tile_done_colsum(const TileParams& p, int64_t c_local, int64_t tile, double* sm,
+                                                     double* dyn) {
+  __shared__ int s_last;
+  unsigned* tick = p.tickets + c_local * (p.tree.nodes + 1);
+  double* nodes = p.nodes + c_local * p.tree.nodes * p.n;
+  const double* level_src = p.partial + c_local * p.tiles * p.n;  // vectors of the current level
+  int64_t node = tile;
+  for (int level = 0;; ++level) {
+    const bool top = level == p.tree.levels;
+    const int64_t parent = top ? 0 : node / TREE_RADIX;
+    const int64_t first = parent * TREE_RADIX;
+    const int64_t expected = top ? p.tree.count[level] : min(static_cast<int64_t>(TREE_RADIX), p.tree.count[level] - first);
+    unsigned* t = top ? tick + p.tree.nodes : tick + p.tree.off[level + 1] + parent;
+    // release pattern of a grid barrier: the CTA's writes are ordered before the barrier, thread 0's fence
+    // is cumulative over what it has observed, so the vector is visible device-wide before the ticket is
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const bool last = atomicAdd(t, 1u) == static_cast<unsigned>(expected - 1);
+      if (last) __threadfence();  // acquire side: the other CTAs' vectors are read next
+      s_last = last;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (top) {
+      finish_contract<Real>(p, c_local, level_src, expected, sm, dyn);
+      return;
+    }
+    double* dst = nodes + (p.tree.off[level + 1] + parent) * p.n;
+    fold_vectors(level_src + first * p.n, expected, p.n, sm, [&](int64_t col, double v) { dst[col] = v; });
+    level_src = nodes + p.tree.off[level + 1] * p.n;
+    node = parent;
+  }
+}
+
+// OUT_TERMINAL: the CTA that stores the last tile sum of a contract folds them (fixed order)
+static __device__ SMC_COLD void tile_done_terminal(const TileParams& p, int64_t c_local, double tile_total, int64_t tile,
+                                                       double* sm) {
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    p.term_partial[c_local * p.tiles + tile] = tile_total;
+    __threadfence();
+    s_last = atomicAdd(p.tickets + c_local, 1u) == static_cast<unsigned>(p.tiles - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double s = 0.0;
+  if (threadIdx.x < p.tiles)  // this thread's tiles: threadIdx.x, threadIdx.x + 256, ... (eight loads in flight)
+    s = strided_sum(p.term_partial + c_local * p.tiles + threadIdx.x, (p.tiles - threadIdx.x + CF_BLOCK - 1) / CF_BLOCK, CF_BLOCK);
+  const double tot = block_sum(s, sm);
+  if (threadIdx.x == 0) p.terminal_sum_out[c_local] = tot;
+  __syncthreads();
+}
+
+// phase 2 of the peer exchange (after this rank has pushed everything it will push): wait for every
+// rank's vector of a contract, sum in rank order, transform.
+template <typename Real>
+static __device__ __noinline__ void exchange_collect(const TileParams& p, double* dyn) {
+  __shared__ int s_ok;
+  const PeerExchange& px = p.px;
+  const int64_t n = p.n, cap = px.capacity_contracts;
+  const int64_t slot = px.epoch & 1u;
+  const size_t flag_base = exchange_data_doubles(cap, n, px.world);
+  const size_t status_cell = exchange_status_cell(cap, n, px.world);
+  double* re = dyn;
+  double* im = dyn + n;
+  double* twr = dyn + 2 * n;
+  double* twi = twr + (p.fft_mode == 0 ? n / 2 : n);
+  fill_twiddles(twr, twi, p.fft_mode == 0 ? n / 2 : n, n);
+  const double* mine = px.data[px.rank];
+  for (int64_t c = blockIdx.x; c < p.launch_contracts; c += gridDim.x) {
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if (threadIdx.x < px.world) {
+      const unsigned* flag = reinterpret_cast<const unsigned*>(mine + flag_base + ((slot * px.world + threadIdx.x) * cap + c));
+      if (!wait_for_flag(flag, px, status_cell)) s_ok = 0;
+    }
+    __syncthreads();
+    const bool ok = s_ok != 0;
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      double s = 0.0;
+      for (int q = 0; q < px.world; ++q) s += __ldcv(mine + ((slot * px.world + q) * cap + c) * n + col);
+      int64_t where = col;
+      if (p.fft_mode == 0 && p.log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), p.log2n));
+      re[where] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
+      im[where] = 0.0;
+    }
+    __syncthreads();
+    transform_store<Real>(re, im, twr, twi, n, p.fft_mode, static_cast<Real*>(p.out) + (p.out_contract0 + c) * n * 2);
+    __syncthreads();  // re / im are reused by the next contract of this CTA
+  }
+}
+
+#ifndef SMC_F64_FUSED_MIN_CTAS
+#define SMC_F64_FUSED_MIN_CTAS 4
+#endif
+#ifndef SMC_F32_FUSED_MIN_CTAS_OTHER
+#define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
+#endif
+#ifndef SMC_F32_FUSED_MIN_CTAS_TERMINAL
+#define SMC_F32_FUSED_MIN_CTAS_TERMINAL 4  // log-Euler with staged terminals (NORMALIZE pass A): 1.360 ms at c2 vs 1.445 at 5
+#endif
+#ifndef SMC_F32_FUSED_MIN_CTAS
+#define SMC_F32_FUSED_MIN_CTAS 5  // with SMC_F32X2=1: measured best (1.322 ms vs 1.385 at 4, 1.341 at 6; profiles/r1_codegen_variant_matrix.txt)
+#endif
+// float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
+// registers and run 2 CTAs per SM
+template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER)))
+    step_kernel(const __grid_constant__ TileParams p) {
+  extern __shared__ double dyn[];
+  __shared__ double sm[CF_BLOCK];
+  const int64_t c_local = blockIdx.y + static_cast<int64_t>(blockIdx.z) * 65535;
+  if (c_local >= p.launch_contracts) return;
+  const int64_t tile = blockIdx.x;
+  const int64_t c_global = p.contract0 + c_local;
+  const int64_t row0 = p.row_begin + tile * p.tile_rows;
+  const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
+
+  SimConsts<Real> k{};
+  if (SRC != SRC_MATRIX) k = contract_consts<Real>(p, c_local);
+  const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
+  const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
+
+  const int r = p.chunk_shift >= 0 ? static_cast<int>(threadIdx.x >> p.chunk_shift) : static_cast<int>(threadIdx.x) / p.chunk_w;
+  const int lc = threadIdx.x - r * p.chunk_w;
+  const int64_t local_base = c_local * p.paths_local - p.row_begin * p.n;  // + global path -> staging index
+  double tile_total = 0.0;
+
+  for (int64_t n0 = 0; n0 < p.n; n0 += p.chunk_w) {
+    const int64_t col = n0 + lc;
+    const bool active = (r < p.lanes_r) && (col < p.n);
+    double acc = 0.0;
+    if (active) {
+      for (int64_t row = row0 + r; row < row1; row += p.lanes_r) {
+        const int64_t path = row * p.n + col;  // global path index b*N + n (gbm_trainer.py:814-816)
+        Real val;
+        if (SRC == SRC_FUSED)
+          val = simulate_terminal<SCHEME, RAGGED>(k, static_cast<uint32_t>(path), p.timesteps, p.keys, k_lo, k_hi);
+        else if (SRC == SRC_TERMINAL)
+          val = __ldcs(static_cast<const Real*>(p.terminal_in) + local_base + path);
+        else
+          val = __ldcs(static_cast<const Real*>(p.matrix) + (path - p.row_begin * p.n));
+        if (OUT == OUT_TERMINAL) {
+          static_cast<Real*>(p.terminal_out)[local_base + path] = val;
+          acc += static_cast<double>(val);
+        } else if (SRC == SRC_MATRIX) {
+          acc += static_cast<double>(val);
+        } else {
+          if (p.normalize) val *= k.scale;                              // gbm.py:438
+          const Real diff = k.K - val;
+          const Real put = k.df * (diff > Real(0) ? diff : Real(0));    // gbm.py:473
+          acc += static_cast<double>(put);
+        }
+      }
+    }
+    if (OUT == OUT_COLSUM) {
+      sm[threadIdx.x] = acc;
+      __syncthreads();
+      if (r == 0 && col < p.n) {
+        double s = 0.0;
+        for (int rr = 0; rr < p.lanes_r; ++rr) s += sm[rr * p.chunk_w + lc];
+        p.partial[(c_local * p.tiles + tile) * p.n + col] = s;
+      }
+      __syncthreads();
+    } else {
+      tile_total += acc;
+    }
+  }
+  if (OUT == OUT_COLSUM) {
+    tile_done_colsum<Real>(p, c_local, tile, sm, dyn);
+  } else {
+    const double t = block_sum(tile_total, sm);
+    tile_done_terminal(p, c_local, t, tile, sm);
+  }
+}
+
+// Phase 2 of the peer exchange as a kernel of its own (persistent, co-resident), launched right after a
+// step kernel whose finishing CTAs pushed (FINISH_EXCHANGE).
+template <typename Real>
+__global__ void __launch_bounds__(CF_BLOCK) exchange_collect_kernel(const __grid_constant__ TileParams p) {
+  extern __shared__ double dyn[];
+  exchange_collect<Real>(p, dyn);
+}
+
+// Separate finalise kernel for transforms whose working set does not fit beside the step kernel's
+// CTAs.  One CTA per contract: fold the `groups` top-level vectors (contract c's start at
+// vecs + c * contract_stride), scale, transform, narrow.
 // Shared memory (doubles): re[n], im[n], then the twiddle table (n/2 pairs for radix-2, n pairs for
 // the DFT).  mode: 0 radix-2 (n power of two), 1 table DFT, 2 DFT with on-the-fly twiddles and the
 // folded vector staged in `spill` (global) for n too large for shared memory.
 template <typename Real>
 __global__ void __launch_bounds__(CF_BLOCK)
-    cf_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
-                       int log2n, Real* __restrict__ out /* [contracts, n, 2] */, int64_t out_contract0,
+    cf_finalize_kernel(const double* __restrict__ vecs, int64_t contract_stride, int64_t groups, int64_t n, double scale,
+                       int mode, int log2n, Real* __restrict__ out /* [contracts, n, 2] */, int64_t out_contract0,
                        double* __restrict__ spill) {
   extern __shared__ double smem[];
   const int64_t c = blockIdx.x;
-  const double* src = vecs + c * groups * n;
+  const double* src = vecs + c * contract_stride;
   Real* dst = out + (out_contract0 + c) * n * 2;
 
   if (mode == 2) {
@@ -546,60 +866,33 @@ __global__ void __launch_bounds__(CF_BLOCK)
   transform_store<Real>(re, im, twr, twi, n, mode, dst);
 }
 
-// ---- fused finalise + all-reduce over peer memory (NVLink / NVSwitch) ---------------------------
-// Multi-GPU form of cf_finalize_kernel for batch-sharded RAW runs: instead of transforming its local
+// ---- all-reduce over peer memory (NVLink / NVSwitch) fused into the step -----------------------
+// Multi-GPU form of the contract finish for batch-sharded runs: instead of transforming its local
 // partial sums and handing the complex result to ncclAllReduce, every rank
-//   phase 1  folds its groups into the real length-n vector x_rank (float64, already scaled by
-//            1 / B_total) and STORES it into a slot of every peer's exchange buffer (its own
-//            included), then publishes a per-contract flag on each peer (release, system scope);
-//   phase 2  waits for the flags of all ranks on its own buffer (acquire), sums the `world` vectors in
-//            rank order — every rank forms the identical float64 sum — and takes the ONE transform.
+//   phase 1  (finish_contract, FINISH_EXCHANGE) folds its top-level vectors into the real length-n
+//            vector x_rank (float64, already scaled by 1 / B_total) and STORES it into a slot of every
+//            peer's exchange buffer (its own included), then publishes a per-contract flag on each peer
+//            (release, system scope);
+//   phase 2  (exchange_collect) waits for the flags of all ranks on its own buffer (acquire), sums the
+//            `world` vectors in rank order — every rank forms the identical float64 sum — and takes the
+//            ONE transform.
 // The exchange therefore moves n doubles per contract and rank (half of what the complex all-reduce
-// moves), carries the sum in float64, and costs one launch with no host involvement.
+// moves), carries the sum in float64, and costs no launch and no host involvement.
 // Deadlock freedom: the grid is persistent and never larger than the number of co-resident CTAs;
-// every CTA finishes phase 1 (which never waits) for all of its contracts before it waits in phase 2,
-// so every flag a peer waits for is written by a CTA that is already running.  Slots alternate with the
-// epoch parity: a rank can be at most one call ahead of a peer, because its phase 2 of call k needs
-// that peer's phase 1 of call k.  A wait that exceeds 2^27 polls (about a minute) traps: a diagnosable error, not a hang.
-constexpr int MAX_PEERS = 16;
-
-struct PeerExchange {
-  double* data[MAX_PEERS];     // exchange buffer of rank p as mapped into this process
-  int rank, world;
-  unsigned epoch;              // > 0, the same on every rank for one call, increasing
-  int64_t capacity_contracts;  // contracts the buffers were sized for
-};
-
-// Exchange buffer of one rank, in 8-byte cells:
-//   [2 slots][world senders][capacity contracts][n]   partial column sums          (exchange-finalise kernel)
-//   [2 slots][world senders][capacity contracts]      their per-contract flags
-//   [2 slots][world senders][capacity contracts]      one double per contract      (small all-reduce: terminal sums)
-//   [2 slots][world senders]                          its per-sender flags
-__host__ __device__ inline size_t exchange_data_doubles(int64_t capacity_contracts, int64_t n, int world) {
-  return static_cast<size_t>(2) * world * capacity_contracts * n;
-}
-__host__ __device__ inline size_t exchange_small_base(int64_t capacity_contracts, int64_t n, int world) {
-  return exchange_data_doubles(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts;
-}
-__host__ __device__ inline size_t exchange_total_cells(int64_t capacity_contracts, int64_t n, int world) {
-  return exchange_small_base(capacity_contracts, n, world) + static_cast<size_t>(2) * world * capacity_contracts +
-         static_cast<size_t>(2) * world;
-}
-
-__device__ __forceinline__ void store_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned load_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
+// every CTA leaves the tile loop — where all pushes happen and nothing waits — before it waits in
+// phase 2, so every flag a peer waits for is written by a CTA that is already running.  Slots
+// alternate with the epoch parity: a rank can be at most one call ahead of a peer, because its phase 2
+// of call k needs that peer's phase 1 of call k.  A wait is bounded in TIME (PeerExchange::timeout_ns,
+// default two minutes): a peer that never arrives yields NaN targets and a status word, not a trap.
+//
+// The same two phases as a kernel of their own, for transforms too large to sit in the step kernel:
 template <typename Real>
 __global__ void __launch_bounds__(CF_BLOCK)
-    cf_exchange_finalize_kernel(const double* __restrict__ vecs, int64_t groups, int64_t n, double scale, int mode,
-                                int log2n, Real* __restrict__ out, int64_t contracts, const PeerExchange px) {
+    cf_exchange_finalize_kernel(const double* __restrict__ vecs, int64_t contract_stride, int64_t groups, int64_t n,
+                                double scale, int mode, int log2n, Real* __restrict__ out, int64_t contracts,
+                                const PeerExchange px) {
   extern __shared__ double smem[];
+  __shared__ int s_ok;
   double* re = smem;
   double* im = smem + n;
   double* twr = smem + 2 * n;
@@ -609,10 +902,11 @@ __global__ void __launch_bounds__(CF_BLOCK)
   const int64_t cap = px.capacity_contracts;
   const int64_t slot = px.epoch & 1u;
   const size_t flag_base = exchange_data_doubles(cap, n, px.world);  // flags follow the data (as 8-byte cells)
+  const size_t status_cell = exchange_status_cell(cap, n, px.world);
 
   // phase 1: fold, push to every peer, publish
   for (int64_t c = blockIdx.x; c < contracts; c += gridDim.x) {
-    const double* src = vecs + c * groups * n;
+    const double* src = vecs + c * contract_stride;
     const size_t cell = ((slot * px.world + px.rank) * cap + c);
     for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
       const double x = strided_sum(src + col, groups, n) * scale;
@@ -627,19 +921,20 @@ __global__ void __launch_bounds__(CF_BLOCK)
   // phase 2: wait for every rank's vector of this contract, sum in rank order, transform
   const double* mine = px.data[px.rank];
   for (int64_t c = blockIdx.x; c < contracts; c += gridDim.x) {
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
     if (threadIdx.x < px.world) {
       const unsigned* flag = reinterpret_cast<const unsigned*>(mine + flag_base + ((slot * px.world + threadIdx.x) * cap + c));
-      unsigned polls = 0;
-      while (load_acquire_sys(flag) != px.epoch)
-        if (++polls > (1u << 27)) __trap();  // about a minute of polling: the peer is gone
+      if (!wait_for_flag(flag, px, status_cell)) s_ok = 0;
     }
     __syncthreads();
+    const bool ok = s_ok != 0;
     for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
       double s = 0.0;
       for (int q = 0; q < px.world; ++q) s += __ldcv(mine + ((slot * px.world + q) * cap + c) * n + col);
       int64_t where = col;
       if (mode == 0 && log2n > 0) where = static_cast<int64_t>(bit_reverse(static_cast<unsigned>(col), log2n));
-      re[where] = s;
+      re[where] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
       im[where] = 0.0;
     }
     __syncthreads();
@@ -653,10 +948,12 @@ __global__ void __launch_bounds__(CF_BLOCK)
 // One CTA (the vector is at most a few thousand doubles); used for the NORMALIZE terminal sums.
 __global__ void __launch_bounds__(CF_BLOCK)
     p2p_allreduce_small_kernel(double* __restrict__ inout, int64_t count, int64_t n, const PeerExchange px) {
+  __shared__ int s_ok;
   const int64_t cap = px.capacity_contracts;
   const int64_t slot = px.epoch & 1u;
   const size_t base = exchange_small_base(cap, n, px.world);
   const size_t flags = base + static_cast<size_t>(2) * px.world * cap;
+  if (threadIdx.x == 0) s_ok = 1;
   for (int64_t i = threadIdx.x; i < count; i += CF_BLOCK) {
     const double v = inout[i];
     for (int p = 0; p < px.world; ++p) px.data[p][base + (slot * px.world + px.rank) * cap + i] = v;
@@ -666,16 +963,15 @@ __global__ void __launch_bounds__(CF_BLOCK)
   if (threadIdx.x < px.world) {
     store_release_sys(reinterpret_cast<unsigned*>(px.data[threadIdx.x] + flags + slot * px.world + px.rank), px.epoch);
     const unsigned* flag = reinterpret_cast<const unsigned*>(px.data[px.rank] + flags + slot * px.world + threadIdx.x);
-    unsigned polls = 0;
-    while (load_acquire_sys(flag) != px.epoch)
-      if (++polls > (1u << 27)) __trap();
+    if (!wait_for_flag(flag, px, exchange_status_cell(cap, n, px.world))) s_ok = 0;
   }
   __syncthreads();
+  const bool ok = s_ok != 0;
   const double* mine = px.data[px.rank] + base;
   for (int64_t i = threadIdx.x; i < count; i += CF_BLOCK) {
     double s = 0.0;
     for (int q = 0; q < px.world; ++q) s += __ldcv(mine + (slot * px.world + q) * cap + i);
-    inout[i] = s;
+    inout[i] = ok ? s : __longlong_as_double(0x7ff8000000000000ll);
   }
 }
 
@@ -687,6 +983,7 @@ constexpr size_t SMEM_LIMIT = 200 * 1024;
 struct FinalizePlan {
   int mode, log2n;
   size_t smem;
+  bool in_step;  // the transform runs inside the step kernel (finish_contract)
 };
 
 static FinalizePlan finalize_plan(int64_t n) {
@@ -707,67 +1004,12 @@ static FinalizePlan finalize_plan(int64_t n) {
     f.log2n = 0;
   }
   if (f.mode == 0 && n == 1) f.smem = 32;
+  static const bool separate = [] {  // diagnostic: SMC_SEPARATE_FINALIZE=1 keeps the transform in its own kernel
+    const char* e = std::getenv("SMC_SEPARATE_FINALIZE");
+    return e && std::atoi(e) != 0;
+  }();
+  f.in_step = f.mode != 2 && f.smem <= FUSED_FINALIZE_SMEM_MAX && !separate;
   return f;
-}
-
-template <typename Real>
-static int launch_finalize(const double* vecs, int64_t contracts, int64_t groups, int64_t n, double scale,
-                           void* out, int64_t out_contract0, double* spill, cudaStream_t st) {
-  const FinalizePlan f = finalize_plan(n);
-  if (f.smem > 48 * 1024)
-    SMC_CUDA_OK(cudaFuncSetAttribute(cf_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(f.smem)));
-  cf_finalize_kernel<Real><<<static_cast<unsigned>(contracts), CF_BLOCK, f.smem, st>>>(
-      vecs, groups, n, scale, f.mode, f.log2n, static_cast<Real*>(out), out_contract0, spill);
-  SMC_LAUNCH_OK("cf_finalize_kernel");
-  return SMC_OK;
-}
-
-template <typename Real, int SRC, int OUT>
-static int launch_tile(TileParams p, int64_t contracts, int scheme, SimConsts<Real>* consts, cudaStream_t st) {
-  if (p.tiles > 0x7fffffffLL) return set_error(SMC_EINVAL, "tile grid too large (%lld)", (long long)p.tiles);
-  p.launch_contracts = contracts;
-  p.consts = consts;
-  p.chunk_shift = (p.chunk_w & (p.chunk_w - 1)) == 0 ? __builtin_ctz(static_cast<unsigned>(p.chunk_w)) : -1;
-  if (SRC != SRC_MATRIX) {
-    prep_consts_kernel<Real><<<static_cast<unsigned>((contracts + CF_BLOCK - 1) / CF_BLOCK), CF_BLOCK, 0, st>>>(p, scheme, consts);
-    SMC_LAUNCH_OK("prep_consts_kernel");
-  }
-  const dim3 grid(static_cast<unsigned>(p.tiles), static_cast<unsigned>(std::min<int64_t>(contracts, 65535)),
-                  static_cast<unsigned>((contracts + 65534) / 65535));
-  // float32 fused kernels exist in two forms: with and without the ragged-tail code (see simulate_path_f32)
-  const bool whole_blocks = SRC == SRC_FUSED && sizeof(Real) == 4 && p.timesteps % 6 == 0;
-  if (SRC != SRC_FUSED || scheme == SMC_LOG_EULER) {
-    if (whole_blocks) tile_kernel<Real, SRC, SMC_LOG_EULER, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
-    else tile_kernel<Real, SRC, SMC_LOG_EULER, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
-  } else if (scheme == SMC_SIMPLE_EULER) {
-    if (whole_blocks) tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
-    else tile_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
-  } else {
-    if (whole_blocks) tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, SRC != SRC_FUSED || sizeof(Real) != 4><<<grid, CF_BLOCK, 0, st>>>(p);
-    else tile_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true><<<grid, CF_BLOCK, 0, st>>>(p);
-  }
-  SMC_LAUNCH_OK("tile_kernel");
-  return SMC_OK;
-}
-
-// column partials -> (optional level 1) -> finalize
-template <typename Real>
-static int reduce_and_finalize(const TilePlan& plan, double* partial, double* grouped, int64_t contracts,
-                               int64_t n, double scale, void* out, int64_t out_contract0, double* spill,
-                               cudaStream_t st) {
-  const double* vecs = partial;
-  int64_t groups = plan.tiles;
-  if (plan.tiles > MAX_GROUPS) {
-    const unsigned grid = static_cast<unsigned>(plan.groups * contracts);
-    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
-    reduce_tiles_kernel<<<grid, CF_BLOCK, 0, st>>>(partial, grouped, plan.tiles, plan.tiles_per_group,
-                                                    plan.groups, n, subs);
-    SMC_LAUNCH_OK("reduce_tiles_kernel");
-    vecs = grouped;
-    groups = plan.groups;
-  }
-  return launch_finalize<Real>(vecs, contracts, groups, n, scale, out, out_contract0, spill, st);
 }
 
 struct Workspace {
@@ -782,13 +1024,21 @@ struct Workspace {
   }
 };
 
-// bytes needed by the column-sum pipeline for `contracts` contracts
+// Control words of one launch: the consts-ready flags followed by the tickets.  They are the only part
+// of the workspace that must be zero when the kernel starts (one cudaMemsetAsync per launch).
 constexpr size_t CONSTS_STRIDE = 64;  // >= sizeof(SimConsts<double>)
 
+static size_t control_bytes(const TilePlan& plan, int64_t contracts, bool colsum) {
+  const size_t tickets = colsum ? static_cast<size_t>(contracts) * (plan.tree.nodes + 1) : static_cast<size_t>(contracts);
+  return align_up((static_cast<size_t>(contracts) + tickets) * sizeof(unsigned));
+}
+
+// bytes needed by the column-sum pipeline for `contracts` contracts
 static size_t colsum_bytes(const TilePlan& plan, int64_t contracts, int64_t n) {
   size_t b = align_up(static_cast<size_t>(contracts) * plan.tiles * n * sizeof(double));
+  b += align_up(static_cast<size_t>(contracts) * plan.tree.nodes * n * sizeof(double));
   b += align_up(static_cast<size_t>(contracts) * CONSTS_STRIDE);
-  if (plan.tiles > MAX_GROUPS) b += align_up(static_cast<size_t>(contracts) * plan.groups * n * sizeof(double));
+  b += control_bytes(plan, contracts, true);
   if (finalize_plan(n).mode == 2) b += align_up(static_cast<size_t>(contracts) * n * sizeof(double));
   return b;
 }
@@ -825,16 +1075,173 @@ static TileParams base_params(const smc_fused_args* a, const TilePlan& plan) {
   p.tiles = plan.tiles;
   p.chunk_w = plan.chunk_w;
   p.lanes_r = plan.lanes_r;
+  p.tree = plan.tree;
+  p.scheme = a->scheme;
   p.keys = make_philox_keys(a->seed);
   p.first_matrix_index = a->first_matrix_index;
+  p.scale = 1.0 / static_cast<double>(a->batches_total);
   return p;
 }
 
+static TilePlan sim_plan(const smc_fused_args* a) {
+  return make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, false, a->timesteps);
+}
+static TilePlan stream_plan(const smc_fused_args* a) {
+  return make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, true);
+}
+
+// co-resident CTAs of a kernel (the peer-exchange collect kernels must never be larger than this)
+static int resident_ctas(const void* kernel, size_t smem, int64_t* resident) {
+  int per_sm = 0;
+  SMC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CF_BLOCK, smem));
+  *resident = static_cast<int64_t>(per_sm) * sm_count();
+  SMC_REQUIRE(*resident > 0, "the kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+  return SMC_OK;
+}
+
+template <typename Kernel>
+static int launch_one(Kernel kernel, const TileParams& p, size_t smem, cudaStream_t st) {
+  const dim3 grid(static_cast<unsigned>(p.tiles), static_cast<unsigned>(std::min<int64_t>(p.launch_contracts, 65535)),
+                  static_cast<unsigned>((p.launch_contracts + 65534) / 65535));
+  kernel<<<grid, CF_BLOCK, smem, st>>>(p);
+  SMC_LAUNCH_OK("step_kernel");
+  return SMC_OK;
+}
+
+// Launches the step kernel over `contracts` contracts: one CTA per (contract, tile).  `ctl` is
+// control_bytes() of workspace, `consts` CONSTS_STRIDE bytes per contract; the rest of `p` (sources,
+// outputs, finish) is filled in by the caller.
+template <typename Real, int SRC, int OUT>
+static int launch_step(TileParams p, int64_t contracts, const FinalizePlan& f, void* ctl, size_t ctl_bytes, void* consts,
+                       cudaStream_t st) {
+  if (p.tiles > 0x7fffffffLL) return set_error(SMC_EINVAL, "tile grid too large (%lld)", (long long)p.tiles);
+  p.launch_contracts = contracts;
+  p.chunk_shift = (p.chunk_w & (p.chunk_w - 1)) == 0 ? __builtin_ctz(static_cast<unsigned>(p.chunk_w)) : -1;
+  p.consts = consts;
+  p.consts_ready = static_cast<unsigned*>(ctl);
+  p.tickets = static_cast<unsigned*>(ctl) + contracts;
+  p.fft_mode = f.mode;
+  p.log2n = f.log2n;
+  SMC_CUDA_OK(cudaMemsetAsync(ctl, 0, ctl_bytes, st));
+  const size_t smem = (OUT == OUT_COLSUM && p.finish == FINISH_TRANSFORM) ? f.smem : 0;
+  // float32 fused kernels exist in two forms: with and without the ragged-tail code (see simulate_path_f32)
+  if constexpr (SRC != SRC_FUSED) {
+    return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
+  } else if constexpr (sizeof(Real) == 8) {
+    if (p.scheme == SMC_LOG_EULER) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
+    if (p.scheme == SMC_SIMPLE_EULER) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true>, p, smem, st);
+    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true>, p, smem, st);
+  } else {
+    const bool whole_blocks = p.timesteps % 6 == 0;
+    if (p.scheme == SMC_LOG_EULER) {
+      if (whole_blocks) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, false>, p, smem, st);
+      return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
+    } else if (p.scheme == SMC_SIMPLE_EULER) {
+      if (whole_blocks) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, false>, p, smem, st);
+      return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true>, p, smem, st);
+    }
+    if (whole_blocks) return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, false>, p, smem, st);
+    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true>, p, smem, st);
+  }
+}
+
+static PeerExchange make_peer_exchange(const smc_p2p_group* g) {
+  PeerExchange px{};
+  for (int q = 0; q < g->world; ++q) px.data[q] = static_cast<double*>(g->buffers[q]);
+  px.rank = g->rank;
+  px.world = g->world;
+  px.epoch = g->epoch;
+  px.capacity_contracts = g->capacity_contracts;
+  static const unsigned long long env_ms = [] {  // SMC_P2P_TIMEOUT_MS overrides the default of two minutes
+    const char* e = std::getenv("SMC_P2P_TIMEOUT_MS");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? static_cast<unsigned long long>(v) : 120000ull;
+  }();
+  px.timeout_ns = (g->timeout_ms > 0 ? static_cast<unsigned long long>(g->timeout_ms) : env_ms) * 1000000ull;
+  return px;
+}
+
+// Column-sum step over `contracts` contracts of `a` (sources already set in `p`): tiles -> ticket tree ->
+// targets in `out` rows out_contract0.., complete (one GPU / NULL group: local sums scaled by 1/B_total;
+// with a peer group: summed over the ranks).  Takes partial / nodes / control / spill from `w`.
+template <typename Real, int SRC>
+static int colsum_step(TileParams p, const TilePlan& plan, int64_t contracts, int64_t n, void* out, int64_t out_contract0,
+                       const smc_p2p_group* g, Workspace& w, cudaStream_t st) {
+  const FinalizePlan f = finalize_plan(n);
+  p.partial = w.take<double>(contracts * plan.tiles * n);
+  p.nodes = plan.tree.nodes ? w.take<double>(contracts * plan.tree.nodes * n) : nullptr;
+  void* consts = w.take<char>(contracts * CONSTS_STRIDE);
+  const size_t ctl_bytes = control_bytes(plan, contracts, true);
+  void* ctl = w.take<char>(ctl_bytes);
+  double* spill = f.mode == 2 ? w.take<double>(contracts * n) : nullptr;
+  p.out = out;
+  p.out_contract0 = out_contract0;
+  p.finish = !f.in_step ? FINISH_NONE : (g ? FINISH_EXCHANGE : FINISH_TRANSFORM);
+  if (g) p.px = make_peer_exchange(g);
+  if (int e = launch_step<Real, SRC, OUT_COLSUM>(p, contracts, f, ctl, ctl_bytes, consts, st)) return e;
+  if (f.in_step && g == nullptr) return SMC_OK;
+  if (f.in_step) {
+    // the finishing CTAs have pushed this rank's vectors; a small co-resident grid collects the peers'
+    p.launch_contracts = contracts;
+    p.fft_mode = f.mode;
+    p.log2n = f.log2n;
+    int64_t resident = 0;
+    if (int e = resident_ctas(reinterpret_cast<const void*>(exchange_collect_kernel<Real>), f.smem, &resident)) return e;
+    exchange_collect_kernel<Real><<<static_cast<unsigned>(std::min<int64_t>(contracts, resident)), CF_BLOCK, f.smem, st>>>(p);
+    SMC_LAUNCH_OK("exchange_collect_kernel");
+    return SMC_OK;
+  }
+  // large transforms: the top-level vectors of every contract -> separate kernel
+  const double* vecs = plan.tree.levels ? p.nodes + plan.tree.off[plan.tree.levels] * n : p.partial;
+  const int64_t stride = (plan.tree.levels ? plan.tree.nodes : plan.tiles) * n;
+  const int64_t groups = plan.tree.count[plan.tree.levels];
+  if (g == nullptr) {
+    if (f.smem > 48 * 1024)
+      SMC_CUDA_OK(cudaFuncSetAttribute(cf_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(f.smem)));
+    cf_finalize_kernel<Real><<<static_cast<unsigned>(contracts), CF_BLOCK, f.smem, st>>>(
+        vecs, stride, groups, n, p.scale, f.mode, f.log2n, static_cast<Real*>(out), out_contract0, spill);
+    SMC_LAUNCH_OK("cf_finalize_kernel");
+    return SMC_OK;
+  }
+  if (f.smem > 48 * 1024)
+    SMC_CUDA_OK(cudaFuncSetAttribute(cf_exchange_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(f.smem)));
+  int64_t resident = 0;
+  if (int e = resident_ctas(reinterpret_cast<const void*>(cf_exchange_finalize_kernel<Real>), f.smem, &resident)) return e;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(contracts, resident));  // co-resident: see the kernel
+  cf_exchange_finalize_kernel<Real><<<grid, CF_BLOCK, f.smem, st>>>(
+      vecs, stride, groups, n, p.scale, f.mode, f.log2n, static_cast<Real*>(out) + out_contract0 * n * 2, contracts, p.px);
+  SMC_LAUNCH_OK("cf_exchange_finalize_kernel");
+  return SMC_OK;
+}
+
+// Terminal staging step (NORMALIZE pass A): simulate, store terminals, per-contract local sums.
+template <typename Real>
+static int terminal_step(TileParams p, const TilePlan& plan, int64_t contracts, void* terminal, double* terminal_sum,
+                         Workspace& w, cudaStream_t st) {
+  p.term_partial = w.take<double>(contracts * plan.tiles);
+  void* consts = w.take<char>(contracts * CONSTS_STRIDE);
+  const size_t ctl_bytes = control_bytes(plan, contracts, false);
+  void* ctl = w.take<char>(ctl_bytes);
+  p.terminal_out = terminal;
+  p.terminal_sum_out = terminal_sum;
+  p.finish = FINISH_NONE;
+  return launch_step<Real, SRC_FUSED, OUT_TERMINAL>(p, contracts, FinalizePlan{}, ctl, ctl_bytes, consts, st);
+}
+
+static size_t terminal_step_bytes(const TilePlan& plan, int64_t contracts) {
+  return align_up(static_cast<size_t>(contracts) * plan.tiles * sizeof(double)) + align_up(static_cast<size_t>(contracts) * CONSTS_STRIDE) +
+         control_bytes(plan, contracts, false);
+}
+
 // contracts per pass of the single-GPU NORMALIZE path, given the bytes left for staging
-static size_t normalize_bytes_per_contract(const smc_fused_args* a, const TilePlan& sim_plan, const TilePlan& pay_plan) {
+static size_t normalize_bytes_per_contract(const smc_fused_args* a, const TilePlan& simp, const TilePlan& pay_plan) {
   const int64_t rows = a->batch_end - a->batch_begin;
   return align_up(static_cast<size_t>(rows) * a->network_size * real_size(a->dtype)) +
-         colsum_bytes(pay_plan, 1, a->network_size) + align_up(sim_plan.tiles * sizeof(double)) + 512;
+         colsum_bytes(pay_plan, 1, a->network_size) + terminal_step_bytes(simp, 1) + 512;
+}
+
+static bool valid_shape(const smc_fused_args* a) {
+  return a != nullptr && a->n_contracts > 0 && a->network_size > 0 && a->batch_end > a->batch_begin && a->timesteps > 0;
 }
 
 }  // namespace smc
@@ -842,45 +1249,49 @@ static size_t normalize_bytes_per_contract(const smc_fused_args* a, const TilePl
 using namespace smc;
 
 extern "C" size_t smc_cf_fused_workspace_bytes(const smc_fused_args* a) {
-  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
-  const int64_t rows = a->batch_end - a->batch_begin;
-  const TilePlan plan = make_plan(a->n_contracts, rows, a->network_size);
+  if (!valid_shape(a)) return 0;
+  const TilePlan plan = sim_plan(a);
   if (a->normalization == SMC_RAW) return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
   // NORMALIZE: stage terminals; cap the staging at 8 GiB by chunking contracts
-  const size_t per = normalize_bytes_per_contract(a, plan, make_plan(a->n_contracts, rows, a->network_size, true));
+  const size_t per = normalize_bytes_per_contract(a, plan, stream_plan(a));
   const size_t cap = size_t(8) << 30;
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(a->n_contracts, static_cast<int64_t>(cap / per)));
   return per * chunk + align_up(a->n_contracts * sizeof(double)) + 256;
 }
 
 extern "C" int smc_cf_fused_launch_count(const smc_fused_args* a) {
-  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
-  const int reduce = plan.tiles > MAX_GROUPS ? 1 : 0;
-  if (a->normalization == SMC_RAW) return 3 + reduce;  // prep + tile + [reduce] + finalize
-  const int reduce_pay = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, true).tiles > MAX_GROUPS ? 1 : 0;
-  return 6 + reduce_pay;  // (prep + terminal tile) + terminal sum + (prep + payoff tile) + [reduce] + finalize (per chunk)
+  if (!valid_shape(a)) return 0;
+  const int separate = finalize_plan(a->network_size).in_step ? 0 : 1;
+  if (a->normalization == SMC_RAW) return 1 + separate;  // the step kernel (+ the transform kernel for large N)
+  return 2 + separate;  // terminal step + payoff step (+ transform), per chunk of contracts
+}
+
+// introspection: how the simulation of these arguments is cut into CTAs (no device access)
+extern "C" int smc_cf_fused_plan(const smc_fused_args* a, int64_t* out, int capacity) {
+  clear_error();
+  if (int e = check_args("smc_cf_fused_plan", a)) return e;
+  const TilePlan plan = sim_plan(a);
+  SMC_REQUIRE(out != nullptr && capacity >= 5, "smc_cf_fused_plan: out needs 5 entries");
+  out[0] = plan.tiles;
+  out[1] = plan.tile_rows;
+  out[2] = plan.lanes_r;
+  out[3] = plan.tree.levels;
+  out[4] = plan.tree.count[plan.tree.levels];
+  return SMC_OK;
 }
 
 template <typename Real>
-static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int cf_fused_impl(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t rows = a->batch_end - a->batch_begin;
   const int64_t n = a->network_size;
-  const TilePlan plan = make_plan(a->n_contracts, rows, n);
-  const double scale = 1.0 / static_cast<double>(a->batches_total);
+  const TilePlan plan = sim_plan(a);
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};
 
   if (a->normalization == SMC_RAW) {
     if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
       return set_error(SMC_EWORKSPACE, "smc_cf_fused: workspace %zu < %zu", ws_bytes,
                        colsum_bytes(plan, a->n_contracts, n));
-    TileParams p = base_params(a, plan);
-    p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
-    SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
-    double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
-    double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
-    if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
-    return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n, scale, cf_out, 0, spill, st);
+    return colsum_step<Real, SRC_FUSED>(base_params(a, plan), plan, a->n_contracts, n, cf_out, 0, g, w, st);
   }
 
   // NORMALIZE on one device: needs the mean over ALL paths of a contract
@@ -888,7 +1299,7 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
     return set_error(SMC_EINVAL,
                      "smc_cf_fused: NORMALIZE over a batch shard needs the global terminal mean; use "
                      "smc_fused_terminal + allreduce + smc_cf_from_terminal");
-  const TilePlan pay_plan = make_plan(a->n_contracts, rows, n, true);
+  const TilePlan pay_plan = stream_plan(a);
   double* term_sum = w.take<double>(a->n_contracts);
   const size_t avail = ws_bytes > w.used ? ws_bytes - w.used : 0;
   const int64_t chunk = std::min<int64_t>(
@@ -900,24 +1311,14 @@ static int cf_fused_impl(const smc_fused_args* a, void* cf_out, void* ws, size_t
     w.used = mark;
     TileParams p = base_params(a, plan);
     p.contract0 = c0;
-    Real* staging = w.take<Real>(cc * p.paths_local);
-    p.term_partial = w.take<double>(cc * plan.tiles);
-    double* partial = w.take<double>(cc * pay_plan.tiles * n);
-    SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(cc * CONSTS_STRIDE));
-    double* grouped = pay_plan.tiles > MAX_GROUPS ? w.take<double>(cc * pay_plan.groups * n) : nullptr;
-    double* spill = finalize_plan(n).mode == 2 ? w.take<double>(cc * n) : nullptr;
-    p.terminal_out = staging;
-    if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, cc, a->scheme, consts, st)) return e;
-    terminal_sum_kernel<<<static_cast<unsigned>(cc), CF_BLOCK, 0, st>>>(p.term_partial, term_sum + c0, plan.tiles);
-    SMC_LAUNCH_OK("terminal_sum_kernel");
+    Real* staging = w.take<Real>(cc * rows * n);
+    if (int e = terminal_step<Real>(p, plan, cc, staging, term_sum + c0, w, st)) return e;
     TileParams pb = base_params(a, pay_plan);
     pb.contract0 = c0;
-    pb.partial = partial;
     pb.terminal_in = staging;
     pb.terminal_sum = term_sum + c0;
     pb.normalize = 1;
-    if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(pb, cc, a->scheme, consts, st)) return e;
-    if (int e = reduce_and_finalize<Real>(pay_plan, partial, grouped, cc, n, scale, cf_out, c0, spill, st)) return e;
+    if (int e = colsum_step<Real, SRC_TERMINAL>(pb, pay_plan, cc, n, cf_out, c0, nullptr, w, st)) return e;
   }
   return SMC_OK;
 }
@@ -927,11 +1328,11 @@ extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, siz
   if (int e = check_args("smc_cf_fused", a)) return e;
   SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr, "smc_cf_fused: NULL pointer");
   SMC_REQUIRE(ws != nullptr, "smc_cf_fused: workspace is NULL");
-  return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, cf_out, ws, ws_bytes, as_stream(stream))
-                             : cf_fused_impl<double>(a, cf_out, ws, ws_bytes, as_stream(stream));
+  return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, nullptr, cf_out, ws, ws_bytes, as_stream(stream))
+                             : cf_fused_impl<double>(a, nullptr, cf_out, ws, ws_bytes, as_stream(stream));
 }
 
-// ---- batch-sharded RAW with the all-reduce fused into the finalise kernel (peer memory) ------------
+// ---- batch-sharded RAW with the all-reduce fused into the step kernel (peer memory) ----------------
 extern "C" size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world) {
   if (capacity_contracts <= 0 || network_size <= 0 || world <= 0 || world > MAX_PEERS) return 0;
   return exchange_total_cells(capacity_contracts, network_size, world) * sizeof(double);
@@ -969,114 +1370,76 @@ extern "C" int smc_p2p_free(void* ptr) {
   return SMC_OK;
 }
 
-static PeerExchange make_peer_exchange(const smc_p2p_group* g) {
-  PeerExchange px{};
-  for (int q = 0; q < g->world; ++q) px.data[q] = static_cast<double*>(g->buffers[q]);
-  px.rank = g->rank;
-  px.world = g->world;
-  px.epoch = g->epoch;
-  px.capacity_contracts = g->capacity_contracts;
-  return px;
-}
-
-static int check_group(const char* fn, const smc_fused_args* a, const smc_p2p_group* g) {
+static int check_group_only(const char* fn, const smc_p2p_group* g) {
   SMC_REQUIRE(g != nullptr, "%s: group is NULL", fn);
   SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world, "%s: bad rank %d of %d", fn,
               g->rank, g->world);
   SMC_REQUIRE(g->epoch > 0, "%s: epoch must be > 0 (zero marks an unwritten flag)", fn);
-  SMC_REQUIRE(a->n_contracts <= g->capacity_contracts && a->network_size == g->network_size,
-              "%s: exchange buffers sized for %lld contracts x %lld, call has %lld x %lld", fn,
-              (long long)g->capacity_contracts, (long long)g->network_size, (long long)a->n_contracts,
-              (long long)a->network_size);
+  SMC_REQUIRE(g->capacity_contracts > 0 && g->network_size > 0, "%s: bad buffer shape", fn);
   for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "%s: buffer of rank %d is NULL", fn, q);
   return SMC_OK;
 }
 
-// tile partials -> (optional level 1) -> persistent exchange + finalise kernel
-template <typename Real>
-static int reduce_and_exchange_finalize(const TilePlan& plan, const FinalizePlan& f, double* partial, double* grouped,
-                                        const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, cudaStream_t st) {
-  const int64_t n = a->network_size;
-  const double* vecs = partial;
-  int64_t groups = plan.tiles;
-  if (plan.tiles > MAX_GROUPS) {
-    const int subs = (n <= CF_BLOCK / 2 && CF_BLOCK % n == 0) ? static_cast<int>(CF_BLOCK / n) : 1;
-    reduce_tiles_kernel<<<static_cast<unsigned>(plan.groups * a->n_contracts), CF_BLOCK, 0, st>>>(
-        partial, grouped, plan.tiles, plan.tiles_per_group, plan.groups, n, subs);
-    SMC_LAUNCH_OK("reduce_tiles_kernel");
-    vecs = grouped;
-    groups = plan.groups;
-  }
-  if (f.smem > 48 * 1024)
-    SMC_CUDA_OK(cudaFuncSetAttribute(cf_exchange_finalize_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(f.smem)));
-  int per_sm = 0;
-  SMC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cf_exchange_finalize_kernel<Real>, CF_BLOCK, f.smem));
-  const int64_t resident = static_cast<int64_t>(per_sm) * sm_count();
-  SMC_REQUIRE(resident > 0, "peer exchange: the exchange kernel does not fit on an SM");
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(a->n_contracts, resident));  // co-resident: see the kernel
-  cf_exchange_finalize_kernel<Real><<<grid, CF_BLOCK, f.smem, st>>>(
-      vecs, groups, n, 1.0 / static_cast<double>(a->batches_total), f.mode, f.log2n, static_cast<Real*>(cf_out),
-      a->n_contracts, make_peer_exchange(g));
-  SMC_LAUNCH_OK("cf_exchange_finalize_kernel");
+static int check_group(const char* fn, const smc_fused_args* a, const smc_p2p_group* g) {
+  if (int e = check_group_only(fn, g)) return e;
+  SMC_REQUIRE(a->n_contracts <= g->capacity_contracts && a->network_size == g->network_size,
+              "%s: exchange buffers sized for %lld contracts x %lld, call has %lld x %lld", fn,
+              (long long)g->capacity_contracts, (long long)g->network_size, (long long)a->n_contracts,
+              (long long)a->network_size);
   return SMC_OK;
 }
 
-template <typename Real>
-static int cf_fused_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
-                             cudaStream_t st) {
-  const int64_t rows = a->batch_end - a->batch_begin;
-  const int64_t n = a->network_size;
-  const TilePlan plan = make_plan(a->n_contracts, rows, n);
-  const FinalizePlan f = finalize_plan(n);
-  if (f.mode == 2) return set_error(SMC_EUNSUPPORTED, "smc_cf_fused_p2p: network_size %lld needs the spill transform", (long long)n);
-  if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
-    return set_error(SMC_EWORKSPACE, "smc_cf_fused_p2p: workspace %zu < %zu", ws_bytes, colsum_bytes(plan, a->n_contracts, n));
-  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
-  TileParams p = base_params(a, plan);
-  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
-  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
-  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
-  if (int e = launch_tile<Real, SRC_FUSED, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
-  return reduce_and_exchange_finalize<Real>(plan, f, p.partial, grouped, a, g, cf_out, st);
+// Everything smc_cf_fused_p2p would reject, without touching the device: callers validate BEFORE they
+// advance the epoch, so that a host-side failure on one rank cannot put the ranks out of step.
+extern "C" int smc_cf_fused_p2p_check(const smc_fused_args* a, const smc_p2p_group* g, size_t ws_bytes) {
+  clear_error();
+  if (int e = check_args("smc_cf_fused_p2p", a)) return e;
+  SMC_REQUIRE(a->normalization == SMC_RAW,
+              "smc_cf_fused_p2p: NORMALIZE needs the global terminal mean first (smc_fused_terminal + allreduce + smc_cf_from_terminal)");
+  if (int e = check_group("smc_cf_fused_p2p", a, g)) return e;
+  if (finalize_plan(a->network_size).mode == 2)
+    return set_error(SMC_EUNSUPPORTED, "smc_cf_fused_p2p: network_size %lld needs the spill transform", (long long)a->network_size);
+  const size_t need = colsum_bytes(sim_plan(a), a->n_contracts, a->network_size);
+  if (ws_bytes < need) return set_error(SMC_EWORKSPACE, "smc_cf_fused_p2p: workspace %zu < %zu", ws_bytes, need);
+  return SMC_OK;
 }
 
 extern "C" int smc_cf_fused_p2p(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
                                 void* stream) {
+  if (int e = smc_cf_fused_p2p_check(a, g, ws_bytes)) return e;
+  SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr && ws != nullptr, "smc_cf_fused_p2p: NULL pointer");
+  return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
+                             : cf_fused_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
+}
+
+// Epoch of the first call on this rank whose wait for a peer timed out (0: none).  Synchronises `stream`.
+extern "C" int smc_p2p_status(const smc_p2p_group* g, uint32_t* timed_out_epoch, void* stream) {
   clear_error();
-  if (int e = check_args("smc_cf_fused_p2p", a)) return e;
-  SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr && ws != nullptr && g != nullptr, "smc_cf_fused_p2p: NULL pointer");
-  SMC_REQUIRE(a->normalization == SMC_RAW,
-              "smc_cf_fused_p2p: NORMALIZE needs the global terminal mean first (smc_fused_terminal + allreduce + smc_cf_from_terminal)");
-  if (int e = check_group("smc_cf_fused_p2p", a, g)) return e;
-  return a->dtype == SMC_F32 ? cf_fused_p2p_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
-                             : cf_fused_p2p_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
+  SMC_REQUIRE(timed_out_epoch != nullptr && g != nullptr, "smc_p2p_status: NULL pointer");
+  smc_p2p_group probe = *g;
+  if (probe.epoch == 0) probe.epoch = 1;
+  if (int e = check_group_only("smc_p2p_status", &probe)) return e;
+  const double* cell = static_cast<const double*>(g->buffers[g->rank]) +
+                       exchange_status_cell(g->capacity_contracts, g->network_size, g->world);
+  SMC_CUDA_OK(cudaMemcpyAsync(timed_out_epoch, cell, sizeof(uint32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+  SMC_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
+  return SMC_OK;
 }
 
 // ---- two-phase API for batch-sharded NORMALIZE -------------------------------------------
 extern "C" size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* a) {
-  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
-  return align_up(static_cast<size_t>(a->n_contracts) * plan.tiles * sizeof(double)) +
-         align_up(static_cast<size_t>(a->n_contracts) * CONSTS_STRIDE) + 256;
+  if (!valid_shape(a)) return 0;
+  return terminal_step_bytes(sim_plan(a), a->n_contracts) + 256;
 }
 
 template <typename Real>
 static int fused_terminal_impl(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
                                size_t ws_bytes, cudaStream_t st) {
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size);
-  if (ws_bytes < smc_fused_terminal_workspace_bytes(a) - 256)
+  const TilePlan plan = sim_plan(a);
+  if (ws_bytes < terminal_step_bytes(plan, a->n_contracts))
     return set_error(SMC_EWORKSPACE, "smc_fused_terminal: workspace too small");
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};
-  TileParams p = base_params(a, plan);
-  p.term_partial = w.take<double>(a->n_contracts * plan.tiles);
-  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
-  p.terminal_out = terminal;
-  if (int e = launch_tile<Real, SRC_FUSED, OUT_TERMINAL>(p, a->n_contracts, a->scheme, consts, st)) return e;
-  terminal_sum_kernel<<<static_cast<unsigned>(a->n_contracts), CF_BLOCK, 0, st>>>(p.term_partial, terminal_sum,
-                                                                                  plan.tiles);
-  SMC_LAUNCH_OK("terminal_sum_kernel");
-  return SMC_OK;
+  return terminal_step<Real>(base_params(a, plan), plan, a->n_contracts, terminal, terminal_sum, w, st);
 }
 
 extern "C" int smc_fused_terminal(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
@@ -1089,30 +1452,23 @@ extern "C" int smc_fused_terminal(const smc_fused_args* a, void* terminal, doubl
 }
 
 extern "C" size_t smc_cf_from_terminal_workspace_bytes(const smc_fused_args* a) {
-  if (a == nullptr || a->n_contracts <= 0 || a->network_size <= 0 || a->batch_end <= a->batch_begin) return 0;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, a->network_size, true);
-  return colsum_bytes(plan, a->n_contracts, a->network_size) + 256;
+  if (!valid_shape(a)) return 0;
+  return colsum_bytes(stream_plan(a), a->n_contracts, a->network_size) + 256;
 }
 
 template <typename Real>
-static int cf_from_terminal_impl(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
-                                 void* ws, size_t ws_bytes, cudaStream_t st) {
+static int cf_from_terminal_impl(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal, const double* tsum,
+                                 void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int64_t n = a->network_size;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n, true);
+  const TilePlan plan = stream_plan(a);
   if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
     return set_error(SMC_EWORKSPACE, "smc_cf_from_terminal: workspace too small");
   Workspace w{static_cast<char*>(ws), ws_bytes, 0};
   TileParams p = base_params(a, plan);
-  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
-  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
-  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
-  double* spill = finalize_plan(n).mode == 2 ? w.take<double>(a->n_contracts * n) : nullptr;
   p.terminal_in = terminal;
   p.terminal_sum = tsum;
   p.normalize = tsum != nullptr;
-  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
-  return reduce_and_finalize<Real>(plan, p.partial, grouped, a->n_contracts, n,
-                                   1.0 / static_cast<double>(a->batches_total), cf_out, 0, spill, st);
+  return colsum_step<Real, SRC_TERMINAL>(p, plan, a->n_contracts, n, cf_out, 0, g, w, st);
 }
 
 extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
@@ -1123,44 +1479,21 @@ extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* termina
   SMC_REQUIRE((a->normalization == SMC_NORMALIZE) == (tsum != nullptr),
               "smc_cf_from_terminal: terminal_sum_global must be given iff normalization is NORMALIZE");
   return a->dtype == SMC_F32
-             ? cf_from_terminal_impl<float>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
-             : cf_from_terminal_impl<double>(a, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
+             ? cf_from_terminal_impl<float>(a, nullptr, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
+             : cf_from_terminal_impl<double>(a, nullptr, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
 }
 
 // NORMALIZE over several GPUs without a collective call: smc_fused_terminal, then this in-place sum over
 // ranks of the per-contract terminal sums, then smc_cf_from_terminal_p2p.
 extern "C" int smc_p2p_allreduce_sum_f64(double* inout, int64_t count, const smc_p2p_group* g, void* stream) {
   clear_error();
-  SMC_REQUIRE(inout != nullptr && g != nullptr && count > 0, "smc_p2p_allreduce_sum_f64: bad argument");
-  SMC_REQUIRE(g->world >= 1 && g->world <= MAX_PEERS && g->rank >= 0 && g->rank < g->world,
-              "smc_p2p_allreduce_sum_f64: bad rank %d of %d", g->rank, g->world);
-  SMC_REQUIRE(g->epoch > 0 && count <= g->capacity_contracts, "smc_p2p_allreduce_sum_f64: %lld values, buffers hold %lld (epoch %u)",
-              (long long)count, (long long)g->capacity_contracts, g->epoch);
-  for (int q = 0; q < g->world; ++q) SMC_REQUIRE(g->buffers[q] != nullptr, "smc_p2p_allreduce_sum_f64: buffer of rank %d is NULL", q);
+  SMC_REQUIRE(inout != nullptr && count > 0, "smc_p2p_allreduce_sum_f64: bad argument");
+  if (int e = check_group_only("smc_p2p_allreduce_sum_f64", g)) return e;
+  SMC_REQUIRE(count <= g->capacity_contracts, "smc_p2p_allreduce_sum_f64: %lld values, buffers hold %lld",
+              (long long)count, (long long)g->capacity_contracts);
   p2p_allreduce_small_kernel<<<1, CF_BLOCK, 0, as_stream(stream)>>>(inout, count, g->network_size, make_peer_exchange(g));
   SMC_LAUNCH_OK("p2p_allreduce_small_kernel");
   return SMC_OK;
-}
-
-template <typename Real>
-static int cf_from_terminal_p2p_impl(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal, const double* tsum,
-                                     void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const int64_t n = a->network_size;
-  const TilePlan plan = make_plan(a->n_contracts, a->batch_end - a->batch_begin, n, true);
-  const FinalizePlan f = finalize_plan(n);
-  if (f.mode == 2) return set_error(SMC_EUNSUPPORTED, "smc_cf_from_terminal_p2p: network_size %lld needs the spill transform", (long long)n);
-  if (ws_bytes < colsum_bytes(plan, a->n_contracts, n))
-    return set_error(SMC_EWORKSPACE, "smc_cf_from_terminal_p2p: workspace too small");
-  Workspace w{static_cast<char*>(ws), ws_bytes, 0};
-  TileParams p = base_params(a, plan);
-  p.partial = w.take<double>(a->n_contracts * plan.tiles * n);
-  SimConsts<Real>* consts = reinterpret_cast<SimConsts<Real>*>(w.take<char>(a->n_contracts * CONSTS_STRIDE));
-  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(a->n_contracts * plan.groups * n) : nullptr;
-  p.terminal_in = terminal;
-  p.terminal_sum = tsum;
-  p.normalize = tsum != nullptr;
-  if (int e = launch_tile<Real, SRC_TERMINAL, OUT_COLSUM>(p, a->n_contracts, a->scheme, consts, st)) return e;
-  return reduce_and_exchange_finalize<Real>(plan, f, p.partial, grouped, a, g, cf_out, st);
 }
 
 extern "C" int smc_cf_from_terminal_p2p(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal,
@@ -1171,9 +1504,11 @@ extern "C" int smc_cf_from_terminal_p2p(const smc_fused_args* a, const smc_p2p_g
   SMC_REQUIRE((a->normalization == SMC_NORMALIZE) == (tsum != nullptr),
               "smc_cf_from_terminal_p2p: terminal_sum_global must be given iff normalization is NORMALIZE");
   if (int e = check_group("smc_cf_from_terminal_p2p", a, g)) return e;
+  if (finalize_plan(a->network_size).mode == 2)
+    return set_error(SMC_EUNSUPPORTED, "smc_cf_from_terminal_p2p: network_size %lld needs the spill transform", (long long)a->network_size);
   return a->dtype == SMC_F32
-             ? cf_from_terminal_p2p_impl<float>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
-             : cf_from_terminal_p2p_impl<double>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
+             ? cf_from_terminal_impl<float>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
+             : cf_from_terminal_impl<double>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
 }
 
 // ---- materialised payoff matrix -> CF -------------------------------------------------------
@@ -1205,17 +1540,11 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   p.tiles = plan.tiles;
   p.chunk_w = plan.chunk_w;
   p.lanes_r = plan.lanes_r;
+  p.tree = plan.tree;
   p.matrix = mat;
-  p.partial = w.take<double>(plan.tiles * n);
-  double* grouped = plan.tiles > MAX_GROUPS ? w.take<double>(plan.groups * n) : nullptr;
-  double* spill = finalize_plan(n).mode == 2 ? w.take<double>(n) : nullptr;
-  const double scale = 1.0 / static_cast<double>(batches);
-  if (dtype == SMC_F32) {
-    if (int e = launch_tile<float, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, nullptr, st)) return e;
-    return reduce_and_finalize<float>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
-  }
-  if (int e = launch_tile<double, SRC_MATRIX, OUT_COLSUM>(p, 1, SMC_LOG_EULER, nullptr, st)) return e;
-  return reduce_and_finalize<double>(plan, p.partial, grouped, 1, n, scale, out, 0, spill, st);
+  p.scale = 1.0 / static_cast<double>(batches);
+  if (dtype == SMC_F32) return colsum_step<float, SRC_MATRIX>(p, plan, 1, n, out, 0, nullptr, w, st);
+  return colsum_step<double, SRC_MATRIX>(p, plan, 1, n, out, 0, nullptr, w, st);
 }
 
 // ---- per-row spectra (the ComputeFFT operator) ----------------------------------------------
@@ -1251,9 +1580,10 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
   void* d_out = base + align_up(cbytes);
   char* rest = base + align_up(cbytes) + align_up(obytes);
   // Pinned host buffers are device-addressable under unified addressing.  For small batches the
-  // two staging copies are pure latency (48 bytes in, 1 KiB out at config c2), so the contracts are
-  // read by the prep kernel, and the targets written by the finalise kernel, straight through the
-  // mapped pointers; pageable memory and large batches take the staged copies.
+  // two staging copies are pure latency (48 bytes in, 1 KiB out at config c2), so the contract rows are
+  // read by the step kernel's CTAs, and the targets written by the finishing CTAs, straight through the
+  // mapped pointers; pageable memory and large batches take the staged copies.  (Every CTA reads a
+  // contract's 48 bytes when it first works on it, so the contracts take the alias only up to 4 KiB.)
   auto device_alias = [](const void* host) -> void* {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
@@ -1262,9 +1592,9 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
     }
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
   };
-  constexpr size_t kZeroCopyMax = 64 << 10;
-  void* c_alias = cbytes <= kZeroCopyMax ? device_alias(contracts_host) : nullptr;
-  void* o_alias = obytes <= kZeroCopyMax ? device_alias(cf_host) : nullptr;
+  constexpr size_t kZeroCopyIn = 4 << 10, kZeroCopyOut = 64 << 10;
+  void* c_alias = cbytes <= kZeroCopyIn ? device_alias(contracts_host) : nullptr;
+  void* o_alias = obytes <= kZeroCopyOut ? device_alias(cf_host) : nullptr;
   smc_fused_args b = *a;
   if (c_alias) {
     b.contracts = static_cast<const double*>(c_alias);

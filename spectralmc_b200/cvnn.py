@@ -217,23 +217,34 @@ class FlatAdam:
     def __init__(self, params: list[nn.Parameter], *, lr: float = 1e-2, betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8) -> None:
         if not params:
             raise ValueError("no parameters")
-        self._params = params
-        self.dtype, self.device = params[0].dtype, params[0].device
+        self._params = params  # ALL parameters, so that state-dict indices line up with torch.optim.Adam(params)
+        live = [p for p in params if p.requires_grad]
+        if not live:
+            raise ValueError("no trainable parameters")
+        self.dtype, self.device = live[0].dtype, live[0].device
         if self.device.type != "cuda":
             raise ValueError("FlatAdam needs CUDA parameters (spectralmc_b200 has no CPU path)")
-        if any(p.dtype != self.dtype or p.device != self.device for p in params):
+        if any(p.dtype != self.dtype or p.device != self.device for p in live):
             raise ValueError("parameters must share one device and dtype")
-        n = sum(p.numel() for p in params)
+        n = sum(p.numel() for p in live)
         self.params = torch.empty(n, dtype=self.dtype, device=self.device)
         self.grads = torch.zeros_like(self.params)
         self.exp_avg = torch.zeros_like(self.params)
         self.exp_avg_sq = torch.zeros_like(self.params)
         self.step = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.hyper = _cabi.AdamArgs(lr, betas[0], betas[1], eps)
-        self._slices: list[tuple[int, int]] = []
+        # frozen parameters (requires_grad=False) are neither flattened nor updated, as torch.optim.Adam skips
+        # them; their slot stays None.  Trainable parameters are updated DENSELY every step: one that receives no
+        # gradient in some step sees a zero gradient (its moments decay and residual momentum still moves it),
+        # whereas eager Adam with zero_grad(set_to_none=True) skips it for that step.  The two agree whenever
+        # every trainable parameter gets a gradient in every step — true for every network cvnn_factory builds.
+        self._slices: list[tuple[int, int] | None] = []
         offset = 0
         with torch.no_grad():
             for p in params:
+                if not p.requires_grad:
+                    self._slices.append(None)
+                    continue
                 k = p.numel()
                 self.params[offset : offset + k].copy_(p.detach().reshape(-1))
                 p.data = self.params[offset : offset + k].view(p.shape)
@@ -249,7 +260,10 @@ class FlatAdam:
         step = float(self.step.item())
         state = {}
         if step > 0:
-            for i, (p, (o, k)) in enumerate(zip(self._params, self._slices)):
+            for i, (p, sl) in enumerate(zip(self._params, self._slices)):
+                if sl is None:
+                    continue
+                o, k = sl
                 state[i] = {"step": torch.tensor(step), "exp_avg": self.exp_avg[o : o + k].view(p.shape).clone(),
                             "exp_avg_sq": self.exp_avg_sq[o : o + k].view(p.shape).clone()}
         group = {"lr": self.hyper.lr, "betas": (self.hyper.beta1, self.hyper.beta2), "eps": self.hyper.eps, "weight_decay": 0,
@@ -265,8 +279,9 @@ class FlatAdam:
         self.step.fill_(int(steps.pop()) if steps else 0)
         self.exp_avg.zero_()
         self.exp_avg_sq.zero_()
-        for i, (o, k) in enumerate(self._slices):
-            if i in sd["state"]:
+        for i, sl in enumerate(self._slices):
+            if sl is not None and i in sd["state"]:
+                o, k = sl
                 self.exp_avg[o : o + k].copy_(sd["state"][i]["exp_avg"].reshape(-1))
                 self.exp_avg_sq[o : o + k].copy_(sd["state"][i]["exp_avg_sq"].reshape(-1))
 

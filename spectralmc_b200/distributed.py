@@ -14,6 +14,7 @@ can exercise the sharding/collective logic under ``gloo`` with a stand-in for th
 
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 from typing import Protocol
 
@@ -81,7 +82,8 @@ class PeerExchange:
     the same number of times (the epoch counter advances in lock-step).
     """
 
-    def __init__(self, capacity_contracts: int, network_size: int, *, group=None) -> None:
+    def __init__(self, capacity_contracts: int, network_size: int, *, group=None, timeout_ms: int = 0) -> None:
+        self._own, self._peers, self.timeout_ms = None, [], int(timeout_ms)  # 0: SMC_P2P_TIMEOUT_MS or two minutes
         if not (dist.is_available() and dist.is_initialized()):
             raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
         self.group = group
@@ -92,17 +94,17 @@ class PeerExchange:
         nbytes = int(_cabi.LIB.smc_p2p_buffer_bytes(capacity_contracts, network_size, self.world))
         # Set-up is collective: every rank takes part in both exchanges below even if its own allocation or
         # mapping failed, so that a failure anywhere raises on ALL ranks instead of leaving the others blocked.
-        self._own, handle, problem = None, None, None
+        handle, problem = None, None
         try:
             self._own, handle = _cabi.p2p_alloc(nbytes)
         except Exception as exc:  # noqa: BLE001 - reported to every rank below
             problem = f"rank {self.rank}: {exc}"
         handles: list[bytes | None] = [None] * self.world
         dist.all_gather_object(handles, handle, group=group)
-        self._peers: list[int] = []
         if problem is None and all(h is not None for h in handles):
             try:
-                self._peers = [self._own if q == self.rank else _cabi.p2p_open(handles[q]) for q in range(self.world)]
+                for q in range(self.world):  # one at a time, so that _release() sees what was opened if one fails
+                    self._peers.append(self._own if q == self.rank else _cabi.p2p_open(handles[q]))
             except Exception as exc:  # noqa: BLE001
                 problem = f"rank {self.rank}: {exc}"
         elif problem is None:
@@ -116,7 +118,7 @@ class PeerExchange:
         dist.barrier(group=group)  # every buffer is zeroed and mapped before anyone writes
 
     def _release(self) -> None:
-        for q, ptr in enumerate(self._peers):
+        for q, ptr in enumerate(self._peers):  # may be a prefix of the ranks if the set-up failed part-way
             if q != self.rank:
                 _cabi.LIB.smc_p2p_close(ptr)
         self._peers = []
@@ -124,14 +126,53 @@ class PeerExchange:
             _cabi.LIB.smc_p2p_free(self._own)
             self._own = None
 
-    def next_group(self) -> "_cabi.P2PGroup":
-        self.epoch += 1
+    def _group_at(self, epoch: int) -> "_cabi.P2PGroup":
         g = _cabi.P2PGroup()
         g.rank, g.world = self.rank, self.world
         for q, ptr in enumerate(self._peers):
             g.buffers[q] = ptr
-        g.capacity_contracts, g.network_size, g.epoch = self.capacity_contracts, self.network_size, self.epoch
+        g.capacity_contracts, g.network_size, g.epoch = self.capacity_contracts, self.network_size, epoch
+        g.timeout_ms = self.timeout_ms
         return g
+
+    def peek_group(self) -> "_cabi.P2PGroup":
+        """The group of the NEXT exchange, without advancing the epoch: everything that can fail on the host
+        (argument checks, workspace and output allocation) is done against this, and only then ``commit()``
+        advances — a rank whose call raises before the launch stays in step with its peers."""
+        return self._group_at(self.epoch + 1)
+
+    def commit(self) -> None:
+        self.epoch += 1
+
+    def next_group(self) -> "_cabi.P2PGroup":
+        self.commit()
+        return self._group_at(self.epoch)
+
+    def cf_fused(self, args: "_cabi.FusedArgs", device: torch.device, dtype: torch.dtype,
+                 workspace: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``smc_cf_fused_p2p`` with the epoch advanced only once the call can no longer fail on the host."""
+        group = self.peek_group()
+        need = int(_cabi.LIB.smc_cf_fused_workspace_bytes(_cabi.byref(args)))
+        _cabi.check(_cabi.LIB.smc_cf_fused_p2p_check(_cabi.byref(args), _cabi.byref(group), need))
+        ws = workspace if workspace is not None and workspace.numel() >= need else torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+        if out is None:
+            out = torch.empty((args.n_contracts, args.network_size), dtype=_cabi.complex_dtype(dtype), device=device)
+        self.commit()
+        return _cabi.cf_fused_p2p(args, group, device, dtype, ws, out=out)
+
+    def timed_out_epoch(self) -> int:
+        """Epoch of the first exchange on this rank that gave up waiting for a peer (0: none).  The targets of
+        that call are NaN.  Synchronises the current stream."""
+        status = ctypes.c_uint32(0)
+        group = self._group_at(max(self.epoch, 1))
+        _cabi.check(_cabi.LIB.smc_p2p_status(_cabi.byref(group), ctypes.byref(status), _cabi.stream_handle(None)))
+        return int(status.value)
+
+    def check(self) -> None:
+        epoch = self.timed_out_epoch()
+        if epoch:
+            raise RuntimeError(f"peer exchange: rank {self.rank} timed out waiting for a peer in exchange {epoch} "
+                               f"(of {self.epoch}); the targets of that call are NaN")
 
     def close(self) -> None:
         if self._peers:
@@ -161,6 +202,12 @@ def sharded_cf_targets(
     batch dimension sharded over the ranks of ``group``.  Every rank returns the full result."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    if ops is None:
+        contracts = engine.contract_rows(contracts)  # [C, 6] float64 contiguous on the engine's device, as cf_targets does
+    else:  # a stand-in for the device calls (CPU tests) reads the rows where they are
+        if contracts.dim() != 2 or contracts.shape[1] != 6:
+            raise ValueError(f"contracts must have shape [C, 6]; got {tuple(contracts.shape)}")
+        contracts = contracts.to(torch.float64).contiguous()
     sp = engine._sp
     shard = shard_batches(sp.batches_per_mc_run, world, rank)
     ops = ops or _CabiOps(engine._device, engine._dtype)
@@ -168,7 +215,7 @@ def sharded_cf_targets(
     if engine._cfg.normalization is ForwardNormalization.RAW and exchange is not None and world > 1:
         # all-reduce fused into the finalise kernel over peer memory: no collective call on the data path
         args = engine.fused_args(contracts, n, batch_begin=shard.begin, batch_end=shard.end)
-        out = _cabi.cf_fused_p2p(args, exchange.next_group(), engine._device, engine._dtype)
+        out = exchange.cf_fused(args, engine._device, engine._dtype)
         engine.consume(n)
         return out
     if engine._cfg.normalization is ForwardNormalization.RAW:

@@ -20,6 +20,7 @@ trainer's per-contract loop (gbm_trainer.py:1546-1553).
 
 from __future__ import annotations
 
+import weakref
 from math import exp
 from typing import Annotated, Literal, Sequence, TypeAlias
 
@@ -137,27 +138,30 @@ def build_black_scholes_config(
 
 # ───────────────────────────── kernel launch object ─────────────────────────────
 class _Launch:
-    def __init__(self, blocks: int, threads: int, stream: torch.cuda.Stream | None) -> None:
+    def __init__(self, blocks: int, threads: int, stream: object | None) -> None:
+        # `blocks` is accepted for call compatibility and not used: the grid follows io.shape[1] and the
+        # kernel's vector width (the reference's own total_blocks() is ceil(paths / threads), gbm.py:101-103)
         self._threads, self._stream = threads, stream
 
     def __call__(
-        self, io: torch.Tensor, timesteps: int, dt: float, X0: float, r: float, d: float, v: float, simulate_log_return: bool
+        self, io: object, timesteps: int, dt: float, X0: float, r: float, d: float, v: float, simulate_log_return: bool
     ) -> None:
-        if io.dim() != 2 or io.shape[0] != timesteps:
-            raise ValueError(f"io must have shape (timesteps={timesteps}, paths); got {tuple(io.shape)}")
+        _ptr, shape, _dtype, _keep = _cabi.device_matrix(io, "io")
+        if len(shape) != 2 or shape[0] != timesteps:
+            raise ValueError(f"io must have shape (timesteps={timesteps}, paths); got {tuple(shape)}")
         scheme = _cabi.SMC_LOG_EULER if simulate_log_return else _cabi.SMC_SIMPLE_EULER
-        if self._stream is None:
-            _cabi.gbm_paths_inplace(io, dt, X0, r, d, v, scheme, self._threads)
-        else:
-            with torch.cuda.stream(self._stream):
-                _cabi.gbm_paths_inplace(io, dt, X0, r, d, v, scheme, self._threads)
+        _cabi.gbm_paths_inplace(io, dt, X0, r, d, v, scheme, self._threads, stream=self._stream)
 
 
 class _SimulateBlackScholes:
     """``SimulateBlackScholes[blocks, threads, stream](io, timesteps, dt, X0, r, d, v, log_flag)``.
 
     Same call shape as the reference's Numba kernel object (gbm.py:224-257, launched at
-    gbm.py:413-426 and effects/interpreter.py:645-654).  ``blocks`` is accepted and ignored: the
+    gbm.py:413-426 and effects/interpreter.py:645-654), and it accepts what the reference passes there:
+    ``io`` is a torch CUDA tensor, anything with ``__cuda_array_interface__`` (Numba's
+    ``cuda.as_cuda_array(sims)``, a CuPy array) or a DLPack exporter — zero-copy, mutated in place;
+    ``stream`` is a ``torch.cuda.Stream``, a Numba stream (``.handle``), a CuPy stream (``.ptr``), a raw
+    ``cudaStream_t`` integer, or absent (torch's current stream).  ``blocks`` is accepted and ignored: the
     grid is derived from ``io.shape[1]`` and the vector width; ``threads`` is the CTA size.
     """
 
@@ -229,7 +233,7 @@ class BlackScholes:
         # The materialised pool is created on first use: the fused path never needs it, and at
         # production sizes one matrix is gigabytes.
         self._ngen: Result[ConcurrentNormGenerator, object] | None = None
-        self._host_cache: tuple[tuple[int, int], float, float] | None = None  # ((sims ptr, forwards ptr), F, df_last)
+        self._host_cache: tuple | None = None  # (weakref sims, weakref forwards, F, df_last) of the last _simulate
         self._workspace: torch.Tensor | None = None
 
     # ----------------------------------------------------------------- normal supply
@@ -299,7 +303,9 @@ class BlackScholes:
                 _cabi.normalize_rows(sims, forwards.contiguous())  # gbm.py:437-438
         except _cabi.SmcError as exc:
             return Failure(DeviceKernelFailed(status=exc.code, message=exc.message))
-        self._host_cache = ((sims.data_ptr(), forwards.data_ptr()), float(forwards_h[-1]), float(df_h[-1]))
+        # forwards[-1] / df[-1] on the host for price(), keyed on the IDENTITY of the tensors just made (device
+        # addresses are reused by the caching allocator, so they cannot tell two SimResults apart)
+        self._host_cache = (weakref.ref(sims), weakref.ref(forwards), float(forwards_h[-1]), float(df_h[-1]))
         made = validate_model(self.SimResults, times=times, sims=sims, forwards=forwards, df=df)
         if isinstance(made, Failure):
             raise AssertionError(f"SimResults validation failed: {made.error}")
@@ -313,8 +319,8 @@ class BlackScholes:
         if isinstance(sim_result, Failure):
             return sim_result
         sr = sim_result.value
-        if self._host_cache is not None and self._host_cache[0] == (sr.sims.data_ptr(), sr.forwards.data_ptr()):
-            F_h, df_h = self._host_cache[1], self._host_cache[2]
+        if self._host_cache is not None and self._host_cache[0]() is sr.sims and self._host_cache[1]() is sr.forwards:
+            F_h, df_h = self._host_cache[2], self._host_cache[3]
         else:  # foreign SimResults: one small device->host read
             F_h, df_h = float(sr.forwards[-1].item()), float(sr.df[-1].item())
         np_t = self._np_dtype.type
@@ -393,6 +399,17 @@ class BlackScholes:
         if isinstance(self._ngen, Success):
             self._ngen.value.skip(n_matrices)
 
+    def contract_rows(self, contracts: Sequence["BlackScholes.Inputs"] | torch.Tensor) -> torch.Tensor:
+        """``[C, 6]`` float64 contiguous rows X0,K,T,r,d,v on the engine's device — what the kernels read.
+        Every fused entry point (single-GPU and sharded) coerces through here, so a float32, CPU or strided
+        tensor is converted instead of being read as float64 rows."""
+        if isinstance(contracts, torch.Tensor):
+            if contracts.dim() != 2 or contracts.shape[1] != 6:
+                raise ValueError(f"contracts must have shape [C, 6] (X0, K, T, r, d, v); got {tuple(contracts.shape)}")
+            return contracts.to(device=self._device, dtype=torch.float64).contiguous()
+        host = torch.tensor([[c.X0, c.K, c.T, c.r, c.d, c.v] for c in contracts], dtype=torch.float64).reshape(-1, 6)
+        return host.pin_memory().to(self._device, non_blocking=True)
+
     def cf_targets(self, contracts: Sequence["BlackScholes.Inputs"] | torch.Tensor) -> Result[torch.Tensor, NormalsError]:
         """CF training targets ``[C, N]`` (complex) for a batch of contracts, fully on device.
 
@@ -400,11 +417,7 @@ class BlackScholes:
         contracts])`` (reference gbm_trainer.py:1546-1553, 806-817) with the normals drawn in
         registers.  ``contracts`` may be a ``[C, 6]`` float64 CUDA tensor (columns X0,K,T,r,d,v).
         """
-        if isinstance(contracts, torch.Tensor):
-            rows = contracts.to(device=self._device, dtype=torch.float64).contiguous()
-        else:
-            host = torch.tensor([[c.X0, c.K, c.T, c.r, c.d, c.v] for c in contracts], dtype=torch.float64)
-            rows = host.pin_memory().to(self._device, non_blocking=True)
+        rows = self.contract_rows(contracts)
         n = rows.shape[0]
         if n == 0:
             return Success(torch.empty((0, self._sp.network_size), dtype=_cabi.complex_dtype(self._dtype), device=self._device))

@@ -47,8 +47,10 @@ from torch import nn, optim
 
 from spectralmc_b200.cvnn import FlatAdam, FusedCVNN, describe
 from spectralmc_b200.distributed import PeerExchange, sharded_cf_targets
+from spectralmc_b200 import _cabi
 from spectralmc_b200.errors import (
     DeviceDTypeError,
+    DeviceKernelFailed,
     DeviceNotCUDA,
     InvalidTrainingConfig,
     PredictionFailed,
@@ -239,8 +241,18 @@ class GbmCVNNPricer:
                 if self._exchange is not None:
                     self._exchange.close()
                 self._exchange = PeerExchange(int(dev.shape[0]), self._sp.network_size, group=self._group)  # collective set-up
-            return Success(sharded_cf_targets(self._engine, dev, group=self._group, exchange=self._exchange))
+            try:
+                return Success(sharded_cf_targets(self._engine, dev, group=self._group, exchange=self._exchange))
+            except _cabi.SmcError as exc:  # same error ADT as the single-GPU path (BlackScholes.cf_targets)
+                return Failure(DeviceKernelFailed(status=exc.code, message=exc.message))
         return self._engine.cf_targets(dev)
+
+    def close(self) -> None:
+        """Release the peer-exchange buffers (collective: every rank of the process group must call it).
+        A pricer without a process group has nothing to release."""
+        if self._exchange is not None:
+            exchange, self._exchange = self._exchange, None
+            exchange.close()
 
     def _torch_step(self, real_in, imag_in, targets, optimizer) -> tuple[torch.Tensor, torch.Tensor]:
         """Forward / MSE on real and imaginary parts / backward / Adam (reference :819-835); the
@@ -501,7 +513,6 @@ class _TorchStepGraph:
 
 def _adam_warm_up(scratch: list[torch.Tensor], adam: FlatAdam) -> None:
     """Load the Adam kernels outside a capture, on scratch buffers."""
-    from spectralmc_b200 import _cabi
 
     _cabi.adam_step(scratch[0], scratch[1], scratch[2], scratch[3], torch.zeros(1, dtype=torch.int64, device=adam.device), adam.hyper)
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol() -> None:
 def test_version_and_error_string() -> None:
     from spectralmc_b200 import _cabi
 
-    assert _cabi.version() == 100
+    assert _cabi.version() == 101
     assert isinstance(_cabi.LIB.smc_last_error(), bytes)
 
 
@@ -84,8 +84,8 @@ def test_peer_exchange_argument_validation_needs_no_device() -> None:
     from spectralmc_b200 import _cabi
 
     torch = __import__("torch")
-    # data + per-contract flags + small all-reduce region + its flags, in 8-byte cells
-    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 2) == (2 * 2 * 4 * 16 + 2 * 2 * 4 + 2 * 2 * 4 + 2 * 2) * 8
+    # data + per-contract flags + small all-reduce region + its flags + the status word, in 8-byte cells
+    assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 2) == (2 * 2 * 4 * 16 + 2 * 2 * 4 + 2 * 2 * 4 + 2 * 2 + 1) * 8
     assert _cabi.LIB.smc_p2p_buffer_bytes(4, 16, 17) == 0  # at most 16 peers
     args = _cabi.make_fused_args(None, 4, 12, 16, 64, torch.float32, 0, _cabi.SMC_RAW, 42, 0, batch_begin=0, batch_end=32)
     args.contracts = 16  # any non-NULL value: validation happens before the first device access
@@ -101,5 +101,10 @@ def test_peer_exchange_argument_validation_needs_no_device() -> None:
     group.capacity_contracts, group.rank = 4, 2
     assert call() == 1 and b"bad rank" in _cabi.LIB.smc_last_error()
     group.rank = 0
+    # the device-free pre-flight check callers run BEFORE they advance the epoch sees the same errors
+    check = lambda ws: _cabi.LIB.smc_cf_fused_p2p_check(ctypes.byref(args), ctypes.byref(group), ws)  # noqa: E731
+    assert check(1 << 20) == 0
+    assert check(16) == 3 and b"workspace" in _cabi.LIB.smc_last_error()
     args.normalization = _cabi.SMC_NORMALIZE
     assert call() == 1 and b"NORMALIZE" in _cabi.LIB.smc_last_error()
+    assert check(1 << 20) == 1 and b"NORMALIZE" in _cabi.LIB.smc_last_error()

@@ -1,0 +1,17 @@
+{
+SMC_LIB=tools/tune/lib_r1.so python tools/bench_raw.py c2 c2x8 c2s8
+for v in l0o0 l0o1 l0o2 l1o0 l1o1 l1o2 l1o2c4 l1o2c6 l1o2u2 l0o2c4 l0o2c6; do SMC_LIB=tools/tune/lib_v_$v.so python tools/bench_raw.py c2 c2x8 c2s8; done
+python tools/bench_raw.py c3 c4s
+SMC_SEGMENTS=1 python tools/bench_raw.py c2 c2x8 c2s8
+SMC_SEG_ITEMS=2048 python tools/bench_raw.py c2 c2x8 c2s8
+SMC_SEG_ITEMS=512 python tools/bench_raw.py c2 c2x8 c2s8
+SMC_STATIC_SCHEDULE=1 python tools/bench_raw.py c2
+SMC_SEGMENTS=1 SMC_STATIC_SCHEDULE=1 python tools/bench_raw.py c2
+} > gpurun_out/r2_ab3.log 2>&1
+grep -v "^+" gpurun_out/r2_ab3.log | python -c "
+import sys, json
+for l in sys.stdin:
+    try: d=json.loads(l)
+    except Exception: print(l.strip()); continue
+    print(d['lib'][:24].ljust(24), d['shape'].ljust(5), d['ms_min'], d['ms_med'], d['env'])
+"
