@@ -39,6 +39,9 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 }
 
 #define F32_REFINE_BIT 0x80000000u
+#define F32_SHORT_BIT 0x40000000u /* row-group word of the short-matrix layout (float32, rows <= 3): see oracle/philox.py */
+/* adjacent columns sharing one block */
+static int short_group(int dtype, int64_t rows) { return (dtype == 0 && rows >= 1 && rows <= 3) ? (int)(6 / rows) : 1; }
 static double uniform_21(uint32_t field) { return ((double)field + 0.5) * 0x1p-21; }
 static double uniform_f64(uint32_t hi, uint32_t lo) {
   const uint64_t m = ((uint64_t)(hi & 0xfffffu) << 32) | lo;
@@ -79,6 +82,15 @@ static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, ui
 
 /* K1: the matrix_index-th (rows, cols) matrix; out is float (dtype 0) or double (dtype 1) */
 void oracle_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed, uint64_t matrix_index) {
+  const int G = short_group(dtype, rows);
+  if (G > 1) { /* short layout: element (i, j) = normal (j % G) * rows + i of block j / G */
+    for (int64_t j = 0; j < cols; ++j) {
+      double z[6];
+      normals_block(0, (uint32_t)(j / G), F32_SHORT_BIT, seed, matrix_index, z);
+      for (int64_t i = 0; i < rows; ++i) ((float*)out)[i * cols + j] = (float)z[(j % G) * rows + i];
+    }
+    return;
+  }
   const int per = dtype == 0 ? 6 : 2;
   const int64_t nq = (rows + per - 1) / per;
   for (int64_t j = 0; j < cols; ++j) {
@@ -120,14 +132,21 @@ double oracle_terminal_range(const double* contract, int64_t T, int dtype, int l
   const double dt = Tm / (double)T, sqrt_dt = sqrt(dt); /* gbm.py:411,243 */
   const double drift = log_flag ? r - d - 0.5 * v * v : r - d;
   const int per = dtype == 0 ? 6 : 2;
+  const int G = short_group(dtype, T);
   double tsum = 0.0;
   for (int64_t j = path_begin; j < path_end; ++j) {
     double X = X0;
     for (int64_t q = 0; q * per < T; ++q) {
       double z[6];
-      normals_block(dtype, (uint32_t)j, (uint32_t)q, seed, matrix_index, z);
+      int first = 0;
+      if (G > 1) { /* short layout: the path's T normals sit at (j % G) * T of block j / G */
+        normals_block(0, (uint32_t)(j / G), F32_SHORT_BIT, seed, matrix_index, z);
+        first = (int)(j % G) * (int)T;
+      } else {
+        normals_block(dtype, (uint32_t)j, (uint32_t)q, seed, matrix_index, z);
+      }
       for (int i = 0; i < per && q * per + i < T; ++i) {
-        const double dW = z[i] * sqrt_dt;
+        const double dW = z[first + i] * sqrt_dt;
         if (log_flag) X *= exp(drift * dt + v * dW);
         else X = fabs(X + (drift * X * dt + v * X * dW));
       }

@@ -21,6 +21,13 @@ Stream definition
                   A_2 = (x2 & 0x7ff) << 10 | (x3 >> 2) & 0x3ff
   A zero radius field (probability 2**-21) is refined from word p of a SECOND block with
   counter (j, q | 0x80000000, k lo, k hi): u = ((y_p >> 9) + 0.5) * 2**-44.
+* float32, SHORT matrices (rows <= 3; the reference's own tests run ONE timestep,
+  /root/reference/tests/test_gbm_trainer.py:127-136, tests/test_gbm.py:49-56): a block's six normals
+  would serve a single row of one column, so G = 6 // rows ADJACENT COLUMNS share one block instead:
+  counter = (j // G, 0x40000000, k lo, k hi) — the row-group word carries the short-layout bit, so the two
+  layouts never share a block — and element (i, j) is normal number (j % G) * rows + i of that block
+  (normals 2p, 2p+1 = even / odd value of pair p, as above; refinement counter word 0xC0000000).
+  rows = 1: six columns per block; rows = 2: three; rows = 3: two.  rows = 4, 5 keep the general layout.
 * float64: one block per (column j, row-pair q = i // 2): counter as above with the
   top bit of word 3 set (``0x80000000 | k >> 32``) so the two precisions never share a
   block; (x0, x1) -> 52-bit radius uniform, (x2, x3) -> 52-bit angle uniform, one pair.
@@ -78,6 +85,13 @@ def _key(seed: int) -> tuple[int, int]:
 
 
 F32_REFINE_BIT = 0x80000000
+F32_SHORT_BIT = 0x40000000  # row-group word of the short-matrix layout (rows <= 3)
+
+
+def short_group(rows: int, dtype) -> int:
+    """Adjacent columns sharing one block: 6 // rows for float32 matrices of at most 3 rows, else 1."""
+    return 6 // rows if np.dtype(dtype) == np.float32 and 1 <= rows <= 3 else 1
+
 
 
 def f32_fields(x0, x1, x2, x3):
@@ -136,8 +150,15 @@ def normals_matrix(
     k_lo, k_hi = matrix_index & 0xFFFFFFFF, (matrix_index >> 32) & 0x7FFFFFFF
     key = _key(seed)
     if dtype == np.float32:
-        nq = (rows + 5) // 6
-        q = np.arange(nq, dtype=np.uint32)[:, None]
+        G = short_group(rows, dtype)
+        if G > 1:  # short layout: block index = column // G, one "row group" carrying the short-layout bit
+            g0 = col_begin // G
+            j = np.arange(g0, (col_end + G - 1) // G, dtype=np.uint64).astype(np.uint32)[None, :]
+            nq = 1
+            q = np.full((1, 1), F32_SHORT_BIT, dtype=np.uint32)
+        else:
+            nq = (rows + 5) // 6
+            q = np.arange(nq, dtype=np.uint32)[:, None]
         x = philox4x32_10((j, q, k_lo, k_hi), key)
         radius, angle = f32_fields(*x)
         u1 = [uniform_21(r) for r in radius]
@@ -153,8 +174,15 @@ def normals_matrix(
             ze, zo, r = _box_muller(u1[p], uniform_21(angle[p]))
             zs += [ze, zo]
             rs += [r, r]
-        z = np.stack(zs, axis=1).reshape(6 * nq, -1)[:rows]
-        rad = np.stack(rs, axis=1).reshape(6 * nq, -1)[:rows]
+        z = np.stack(zs, axis=1).reshape(6 * nq, -1)
+        rad = np.stack(rs, axis=1).reshape(6 * nq, -1)
+        if G > 1:  # [6, groups] -> element (i, col) = normal (col % G) * rows + i of group col // G
+            cols_here = np.arange(col_begin, col_end)
+            grp, lane = cols_here // G - g0, cols_here % G
+            pick = lane[None, :] * rows + np.arange(rows)[:, None]
+            z, rad = z[pick, grp[None, :]], rad[pick, grp[None, :]]
+        else:
+            z, rad = z[:rows], rad[:rows]
         z = z.astype(np.float32)
     elif dtype == np.float64:
         nq = (rows + 1) // 2

@@ -40,7 +40,7 @@
 namespace smc {
 
 constexpr int CF_BLOCK = 256;
-constexpr int64_t TARGET_TILES = 16384;
+constexpr int64_t TARGET_TILES = 12288;  // CTAs per launch aimed at (profiles/r2_codegen_variant_matrix.txt: 4096..24576 within 1 %)
 constexpr int64_t STREAM_TILES = 2368;  // 16 x 148
 constexpr int64_t MIN_TILE_PATH_STEPS = 16384;  // a simulated tile is at least 64 path-steps per thread
 constexpr int TREE_RADIX = 16;
@@ -50,7 +50,7 @@ constexpr int SCHEME_LOG_STEPWISE = 2;  // SMC_LOG_EULER_STEPWISE
 constexpr int MAX_PEERS = 16;
 
 #ifndef SMC_TAIL_NOINLINE
-#define SMC_TAIL_NOINLINE 1  // codegen knob: the cold per-tile tail (tickets, folds, transform) as out-of-line functions
+#define SMC_TAIL_NOINLINE 0  // codegen knob: the cold per-tile tail (tickets, folds, transform) as out-of-line functions; inlined measured 0.5-1 % faster at c2 (profiles/r2_codegen_variant_matrix.txt)
 #endif
 #if SMC_TAIL_NOINLINE
 #define SMC_COLD __noinline__
@@ -287,7 +287,7 @@ __device__ __forceinline__ void consume(Real& acc, Real z, const SimConsts<Real>
 // on ptxas' interleaving of IMAD.WIDE / MUFU / LOP3 issue, and merely compiling the tail code into
 // the same kernel costs 2 % at config c2 (A/B in one run: 1.387 vs 1.414 ms), so kernels that
 // cannot have a tail do not contain one.
-template <int SCHEME, bool REFINE, bool RAGGED, bool RAWSUM = false>
+template <int SCHEME, bool REFINE, bool RAGGED>
 __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, uint32_t col, int64_t timesteps,
                                                    const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi,
                                                    uint32_t& min_word) {
@@ -325,7 +325,22 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
       for (int u = 0; u < 6; ++u) consume<float, SCHEME>(acc, z[u], k);
     }
   }
-  if (RAGGED) {  // last block: evaluate only the pairs that are consumed
+  if (RAGGED && timesteps <= 3) {
+    // short layout, one path at a time (the general form, for shapes the grouped tile does not cover): the
+    // path's normals are numbers lane * T .. lane * T + T - 1 of the block its group of G = 6 / T columns shares
+    const uint32_t T = static_cast<uint32_t>(timesteps), G = 6u / T;
+    const uint32_t g = col / G, first = (col - g * G) * T;
+    float z[6];
+    normals6_f32_impl<REFINE, 3>(g, F32_SHORT_BIT, k_lo, k_hi, keys, z, min_word);
+#pragma unroll
+    for (uint32_t i = 0; i < 3; ++i) {
+      if (i < T) {
+        const uint32_t idx = first + i;
+        const float zi = idx == 0 ? z[0] : idx == 1 ? z[1] : idx == 2 ? z[2] : idx == 3 ? z[3] : idx == 4 ? z[4] : z[5];
+        consume<float, SCHEME>(acc, zi, k);
+      }
+    }
+  } else if (RAGGED) {  // last block: evaluate only the pairs that are consumed
     const int rem = static_cast<int>(timesteps - static_cast<int64_t>(nq) * 6);
     if (rem) {
       float z[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -340,8 +355,8 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
         if (u < rem) consume<float, SCHEME>(acc, z[u], k);
     }
   }
-  if (SCHEME == SMC_LOG_EULER && !RAWSUM) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
-  return acc;  // RAWSUM: the sum of the path's normals; the caller applies X0 * 2^(lin0 + lin1 * sum)
+  if (SCHEME == SMC_LOG_EULER) return k.X0 * mufu_ex2(fmaf(k.lin1, acc, k.lin0));
+  return acc;
 }
 
 // the rare re-simulation (some block of the path had a zero radius field): same path with the
@@ -379,34 +394,6 @@ __device__ __forceinline__ float simulate_terminal(const SimConsts<float>& k, ui
 #else
   return simulate_path_f32<SCHEME, true, RAGGED>(k, col, timesteps, keys, k_lo, k_hi, min_word);
 #endif
-}
-
-// Log-Euler float32 only: the SUM of the path's normals, with no per-contract constant in sight, so
-// that the hot loop keeps no constant live in a register; the caller reads X0 / lin0 / lin1 from shared
-// memory afterwards (SMC_CONSTS_LATE).
-template <bool RAGGED>
-static __device__ __noinline__ float simulate_logsum_exact_f32(uint32_t col, int64_t timesteps, uint32_t seed_lo, uint32_t seed_hi,
-                                                              uint32_t k_lo, uint32_t k_hi) {
-  PhiloxKeys keys;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    keys.k0[r] = seed_lo + static_cast<uint32_t>(r) * PHILOX_W0;
-    keys.k1[r] = seed_hi + static_cast<uint32_t>(r) * PHILOX_W1;
-  }
-  const SimConsts<float> none{};
-  uint32_t unused = 0;
-  return simulate_path_f32<SMC_LOG_EULER, true, RAGGED, true>(none, col, timesteps, keys, k_lo, k_hi, unused);
-}
-
-template <bool RAGGED>
-__device__ __forceinline__ float simulate_logsum_f32(uint32_t col, int64_t timesteps, const PhiloxKeys& keys, uint32_t k_lo,
-                                                     uint32_t k_hi) {
-  uint32_t min_word = 0xffffffffu;
-  const SimConsts<float> none{};
-  float s = simulate_path_f32<SMC_LOG_EULER, false, RAGGED, true>(none, col, timesteps, keys, k_lo, k_hi, min_word);
-  if (__builtin_expect(min_word < 2048u, 0))
-    s = simulate_logsum_exact_f32<RAGGED>(col, timesteps, keys.k0[0], keys.k1[0], k_lo, k_hi);
-  return s;
 }
 
 template <int SCHEME, bool RAGGED>
@@ -720,6 +707,74 @@ static __device__ __noinline__ void exchange_collect(const TileParams& p, double
   }
 }
 
+// Short paths (T = timesteps <= 3, float32): G = 6 / T adjacent paths share one Philox block, so a
+// thread draws one block and finishes G paths with it — every normal drawn is consumed, where the general
+// form would spend a whole block (and three Box-Muller pairs) per path.  Thread t of the CTA walks groups
+// g_first + t, g_first + t + 256, ... of the tile's path range and keeps one float64 accumulator per lane
+// of the group; the host takes this form only when 256 G is a multiple of N, so that lane u of thread t
+// stays in ONE column, (g_first G + t G + u) mod N, for the whole tile.  The 256 G accumulators are then
+// folded to the N column sums of the tile in shared memory, in a fixed order.
+template <int SCHEME, int T>
+__device__ __forceinline__ void grouped_short_tile(const TileParams& p, const SimConsts<float>& k, uint32_t k_lo, uint32_t k_hi,
+                                                   int64_t row0, int64_t row1, double* __restrict__ dst, double* sm,
+                                                   double* lanes /* shared, 256 G doubles */) {
+  constexpr int G = 6 / T;
+  const int64_t p0 = row0 * p.n, p1 = row1 * p.n;  // the tile's global paths [p0, p1)
+  const int64_t g_first = p0 / G, g_end = (p1 + G - 1) / G;
+  double acc[G];
+#pragma unroll
+  for (int u = 0; u < G; ++u) acc[u] = 0.0;
+  for (int64_t g = g_first + threadIdx.x; g < g_end; g += CF_BLOCK) {
+    float z[6];
+    uint32_t unused = 0;
+    normals6_f32_impl<true, 3>(static_cast<uint32_t>(g), F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      float state = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
+#pragma unroll
+      for (int i = 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
+      const float val = SCHEME == SMC_LOG_EULER ? k.X0 * mufu_ex2(fmaf(k.lin1, state, k.lin0)) : state;
+      const float diff = k.K - val;
+      const float put = k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
+      const int64_t path = g * G + u;
+      acc[u] += (path >= p0 && path < p1) ? static_cast<double>(put) : 0.0;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < G; ++u) lanes[threadIdx.x * G + u] = acc[u];
+  __syncthreads();
+  // entry e = t G + u belongs to column (o + e) mod N, o = (g_first G) mod N; column `col` owns entries
+  // e0, e0 + N, ... (count per column = 256 G / N).  `subs` threads share a column, then fold in order.
+  const int64_t n = p.n;
+  const int64_t o = (g_first * G) % n;
+  const int64_t per_col = static_cast<int64_t>(CF_BLOCK) * G / n;
+  if (n <= CF_BLOCK) {
+    const int subs = CF_BLOCK / static_cast<int>(n);
+    const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
+    double s = 0.0;
+    if (sub < subs) {
+      const int64_t e0 = (col - o + n) % n;
+      for (int64_t m = sub; m < per_col; m += subs) s += lanes[e0 + m * n];
+    }
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (sub == 0) {
+      double tot = 0.0;
+      for (int q = 0; q < subs; ++q) tot += sm[q * n + col];
+      dst[col] = tot;
+    }
+    __syncthreads();
+  } else {
+    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      const int64_t e0 = (col - o + n) % n;
+      double s = 0.0;
+      for (int64_t m = 0; m < per_col; ++m) s += lanes[e0 + m * n];
+      dst[col] = s;
+    }
+    __syncthreads();
+  }
+}
+
 #ifndef SMC_F64_FUSED_MIN_CTAS
 #define SMC_F64_FUSED_MIN_CTAS 4
 #endif
@@ -730,12 +785,14 @@ static __device__ __noinline__ void exchange_collect(const TileParams& p, double
 #define SMC_F32_FUSED_MIN_CTAS_TERMINAL 4  // log-Euler with staged terminals (NORMALIZE pass A): 1.360 ms at c2 vs 1.445 at 5
 #endif
 #ifndef SMC_F32_FUSED_MIN_CTAS
-#define SMC_F32_FUSED_MIN_CTAS 5  // with SMC_F32X2=1: measured best (1.322 ms vs 1.385 at 4, 1.341 at 6; profiles/r1_codegen_variant_matrix.txt)
+#define SMC_F32_FUSED_MIN_CTAS 6  // round 2 (ticket tail in the kernel): 6 CTAs x 40 registers measured best, 1.309 ms at c2 vs 1.348 at 5 and 1.365 at 4 (profiles/r2_codegen_variant_matrix.txt); round 1 (separate tail kernels) had 5 best
 #endif
 // float64 fused instantiations are capped (4 CTAs = 32 warps per SM): uncapped they take 90
 // registers and run 2 CTAs per SM
-template <typename Real, int SRC, int SCHEME, int OUT, bool RAGGED = true>
-__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER)))
+// FORM (float32 fused kernels): 0 = timesteps a multiple of 6, no tail code in the kernel; 1 = general;
+// 2 = short paths (timesteps <= 3) in the grouped layout, one Philox block per G = 6 / timesteps paths.
+template <typename Real, int SRC, int SCHEME, int OUT, int FORM = 1>
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (FORM == 2 ? SMC_F32_FUSED_MIN_CTAS_OTHER : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER))))
     step_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ double dyn[];
   __shared__ double sm[CF_BLOCK];
@@ -745,11 +802,22 @@ __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real)
   const int64_t c_global = p.contract0 + c_local;
   const int64_t row0 = p.row_begin + tile * p.tile_rows;
   const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
+  constexpr bool RAGGED = FORM != 0;
 
   SimConsts<Real> k{};
   if (SRC != SRC_MATRIX) k = contract_consts<Real>(p, c_local);
   const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
   const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
+
+  if constexpr (FORM == 2 && SRC == SRC_FUSED && OUT == OUT_COLSUM && sizeof(Real) == 4) {
+    __shared__ double lanes[CF_BLOCK * 6];
+    double* dst = p.partial + (c_local * p.tiles + tile) * p.n;
+    if (p.timesteps == 1) grouped_short_tile<SCHEME, 1>(p, k, k_lo, k_hi, row0, row1, dst, sm, lanes);
+    else if (p.timesteps == 2) grouped_short_tile<SCHEME, 2>(p, k, k_lo, k_hi, row0, row1, dst, sm, lanes);
+    else grouped_short_tile<SCHEME, 3>(p, k, k_lo, k_hi, row0, row1, dst, sm, lanes);
+    tile_done_colsum<Real>(p, c_local, tile, sm, dyn);
+    return;
+  }
 
   const int r = p.chunk_shift >= 0 ? static_cast<int>(threadIdx.x >> p.chunk_shift) : static_cast<int>(threadIdx.x) / p.chunk_w;
   const int lc = threadIdx.x - r * p.chunk_w;
@@ -1099,6 +1167,15 @@ static int resident_ctas(const void* kernel, size_t smem, int64_t* resident) {
   return SMC_OK;
 }
 
+// diagnostic: SMC_SHORT_GROUPED=0 sends short paths through the general form (one block per path)
+static bool short_grouped_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("SMC_SHORT_GROUPED");
+    return !(e && std::atoi(e) == 0);
+  }();
+  return on;
+}
+
 template <typename Kernel>
 static int launch_one(Kernel kernel, const TileParams& p, size_t smem, cudaStream_t st) {
   const dim3 grid(static_cast<unsigned>(p.tiles), static_cast<unsigned>(std::min<int64_t>(p.launch_contracts, 65535)),
@@ -1126,22 +1203,28 @@ static int launch_step(TileParams p, int64_t contracts, const FinalizePlan& f, v
   const size_t smem = (OUT == OUT_COLSUM && p.finish == FINISH_TRANSFORM) ? f.smem : 0;
   // float32 fused kernels exist in two forms: with and without the ragged-tail code (see simulate_path_f32)
   if constexpr (SRC != SRC_FUSED) {
-    return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
+    return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, 1>, p, smem, st);
   } else if constexpr (sizeof(Real) == 8) {
-    if (p.scheme == SMC_LOG_EULER) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
-    if (p.scheme == SMC_SIMPLE_EULER) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true>, p, smem, st);
-    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true>, p, smem, st);
+    if (p.scheme == SMC_LOG_EULER) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, 1>, p, smem, st);
+    if (p.scheme == SMC_SIMPLE_EULER) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, 1>, p, smem, st);
+    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, 1>, p, smem, st);
   } else {
-    const bool whole_blocks = p.timesteps % 6 == 0;
+    // FORM: 0 whole 6-row blocks, 1 general, 2 short paths in the grouped layout (COLSUM only; the staging pass of
+    // NORMALIZE and shapes where 256 G is not a multiple of N take the general form, one path at a time)
+    const bool grouped = OUT == OUT_COLSUM && p.timesteps <= 3 && (CF_BLOCK * (6 / p.timesteps)) % p.n == 0 && short_grouped_enabled();
+    const int form = p.timesteps % 6 == 0 ? 0 : (grouped ? 2 : 1);
     if (p.scheme == SMC_LOG_EULER) {
-      if (whole_blocks) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, false>, p, smem, st);
-      return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, true>, p, smem, st);
+      if (form == 0) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, 0>, p, smem, st);
+      if (form == 2) return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT == OUT_COLSUM ? OUT : OUT_COLSUM, OUT == OUT_COLSUM ? 2 : 1>, p, smem, st);
+      return launch_one(step_kernel<Real, SRC, SMC_LOG_EULER, OUT, 1>, p, smem, st);
     } else if (p.scheme == SMC_SIMPLE_EULER) {
-      if (whole_blocks) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, false>, p, smem, st);
-      return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, true>, p, smem, st);
+      if (form == 0) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, 0>, p, smem, st);
+      if (form == 2) return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT == OUT_COLSUM ? OUT : OUT_COLSUM, OUT == OUT_COLSUM ? 2 : 1>, p, smem, st);
+      return launch_one(step_kernel<Real, SRC, SMC_SIMPLE_EULER, OUT, 1>, p, smem, st);
     }
-    if (whole_blocks) return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, false>, p, smem, st);
-    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, true>, p, smem, st);
+    if (form == 0) return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, 0>, p, smem, st);
+    if (form == 2) return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT == OUT_COLSUM ? OUT : OUT_COLSUM, OUT == OUT_COLSUM ? 2 : 1>, p, smem, st);
+    return launch_one(step_kernel<Real, SRC, SCHEME_LOG_STEPWISE, OUT, 1>, p, smem, st);
   }
 }
 

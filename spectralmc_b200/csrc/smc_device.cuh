@@ -96,6 +96,10 @@ __device__ __forceinline__ float mufu_ex2(float x) {
 // counter has the top bit of the row-group word set, extending the tail to 7.9 sigma; it sits
 // behind one rarely-taken branch per block.
 constexpr uint32_t F32_REFINE_BIT = 0x80000000u;
+// Short matrices (float32, rows <= 3; the reference's own tests run ONE timestep): G = 6 / rows adjacent
+// columns share one block — counter (column / G, F32_SHORT_BIT, k lo, k hi) — and element (i, j) is
+// normal (j % G) * rows + i of it, so a block's six normals are all consumed (oracle/philox.py).
+constexpr uint32_t F32_SHORT_BIT = 0x40000000u;
 
 __device__ __forceinline__ float unit_float_21(uint32_t field_in_bits_22_2) {
   return __uint_as_float((field_in_bits_22_2 & 0x007ffffcu) | 0x3f800000u);  // 1 + F 2^-21

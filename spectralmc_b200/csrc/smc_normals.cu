@@ -79,6 +79,25 @@ __global__ void __launch_bounds__(NORMALS_BLOCK, SMC_NORMALS_MIN_CTAS)
   }
 }
 
+// short float32 matrices (ROWS <= 3): one thread per block of G = 6 / ROWS adjacent columns
+template <int ROWS>
+__global__ void __launch_bounds__(NORMALS_BLOCK)
+    philox_normals_f32_short_kernel(float* __restrict__ out, int64_t cols, PhiloxKeys key, uint32_t k_lo, uint32_t k_hi) {
+  constexpr int G = 6 / ROWS;
+  const int64_t g = static_cast<int64_t>(blockIdx.x) * NORMALS_BLOCK + threadIdx.x;
+  const int64_t col0 = g * G;
+  if (col0 >= cols) return;
+  float z[6];
+  normals6_f32(static_cast<uint32_t>(g), F32_SHORT_BIT, k_lo, k_hi, key, z);
+#pragma unroll
+  for (int u = 0; u < G; ++u) {
+    if (col0 + u < cols) {
+#pragma unroll
+      for (int i = 0; i < ROWS; ++i) __stcs(out + i * cols + col0 + u, z[u * ROWS + i]);
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(NORMALS_BLOCK)
     philox_normals_f64_kernel(double* __restrict__ out, int64_t rows, int64_t cols, PhiloxKeys key,
@@ -137,7 +156,14 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
   const char* vec_env = std::getenv("SMC_NORMALS_VEC");
   const int vec_cap = vec_env ? std::atoi(vec_env) : 4;
   const bool allow_vec = vec_cap > 1;
-  if (dtype == SMC_F32) {
+  if (dtype == SMC_F32 && rows <= 3) {  // short layout (oracle/philox.py)
+    const int64_t groups = (cols + 6 / rows - 1) / (6 / rows);
+    const unsigned grid = static_cast<unsigned>((groups + NORMALS_BLOCK - 1) / NORMALS_BLOCK);
+    float* o = static_cast<float*>(out);
+    if (rows == 1) philox_normals_f32_short_kernel<1><<<grid, NORMALS_BLOCK, 0, st>>>(o, cols, key, k_lo, k_hi);
+    else if (rows == 2) philox_normals_f32_short_kernel<2><<<grid, NORMALS_BLOCK, 0, st>>>(o, cols, key, k_lo, k_hi);
+    else philox_normals_f32_short_kernel<3><<<grid, NORMALS_BLOCK, 0, st>>>(o, cols, key, k_lo, k_hi);
+  } else if (dtype == SMC_F32) {
     const bool a8 = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
     int v = 1;
     if (vec_cap >= 4 && aligned16 && cols % 4 == 0) v = 4;

@@ -54,6 +54,9 @@ def _fused(rows, T, N, B, dtype, seed, first_index, scheme, norm, **shard):
 CASES = [
     # T, N, B  — c1 shape, ragged shapes, N > 256, T not a multiple of 4 / 2
     (12, 16, 64), (1, 16, 32), (7, 12, 11), (5, 1, 40), (3, 300, 5), (252, 128, 16), (9, 64, 33), (2, 1024, 3),
+    # short paths (T <= 3) in the grouped layout: several passes per tile, sub-lane folds (N = 48: five lanes per
+    # column), N > 256, and shapes the grouped tile does not cover (256 G not a multiple of N: general form)
+    (1, 128, 100), (2, 64, 70), (3, 32, 50), (1, 48, 37), (1, 512, 7), (1, 20, 33), (2, 3, 500), (4, 16, 40),
 ]
 
 
@@ -72,6 +75,39 @@ def test_fused_matches_oracle(T, N, B, scheme, norm, prec) -> None:
     for c in range(len(rows)):
         assert rel_max(got[c], ref[c]) <= tol, (c, rel_max(got[c], ref[c]))
     assert got.dtype == (np.complex128 if prec == "float64" else np.complex64)
+
+
+@pytest.mark.parametrize("T,N,B", [(1, 16, 4096), (2, 16, 999), (3, 128, 257), (1, 256, 300), (5, 16, 100)])
+@pytest.mark.parametrize("scheme", [_cabi.SMC_LOG_EULER, _cabi.SMC_SIMPLE_EULER, _cabi.SMC_LOG_EULER_STEPWISE])
+def test_short_paths_fused_equals_materialised(T, N, B, scheme) -> None:
+    """T <= 3 uses the short layout of the stream (adjacent columns share a block): the fused kernel, the
+    materialised generator + stepper and the oracle all read the same normals — at the reference's own test
+    size (T = 1, N = 16, B = 4096; tests/test_gbm_trainer.py:127-136) and ragged neighbours; T = 5 is the
+    general layout."""
+    dtype = torch.float32
+    fused = _fused([CANON, ODD], T, N, B, dtype, 77, 3, scheme, _cabi.SMC_RAW)
+    for i, row in enumerate([CANON, ODD]):
+        z = torch.empty((T, N * B), dtype=dtype, device="cuda")
+        _cabi.philox_normals(z, 77, 3 + i)
+        ref_z = philox.normals_matrix(T, N * B, np.float32, 77, 3 + i)
+        assert float(np.max(np.abs(z.cpu().numpy() - ref_z))) <= 4e-6 * (1 + float(np.max(np.abs(ref_z))))
+        X0, K, Tm, r, d, v = row
+        k2 = _cabi.SMC_SIMPLE_EULER if scheme == _cabi.SMC_SIMPLE_EULER else _cabi.SMC_LOG_EULER
+        term = _cabi.gbm_terminal_from_normals(z, Tm / T, X0, r, d, v, k2)
+        put, _ = _cabi.payoff(term, K, math.exp(-r * Tm))
+        mat = _cabi.cf_fft_mean(put.view(B, N)).cpu().numpy()
+        assert rel_max(fused[i], mat) <= 1e-5, (i, rel_max(fused[i], mat))
+
+
+@pytest.mark.parametrize("cuts", [[0, 5, 100], [0, 33, 34, 100], [0, 99, 100]])
+def test_short_paths_shard_at_any_row(cuts) -> None:
+    """Shard boundaries fall inside a group of columns sharing a block (N = 16, G = 6): both shards draw the
+    block and each keeps its own lanes — the partial CFs still add up to the unsharded result."""
+    T, N, B = 1, 16, 100
+    whole = _fused([CANON, ODD], T, N, B, torch.float32, 5, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW)
+    total = sum(_fused([CANON, ODD], T, N, B, torch.float32, 5, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, batch_begin=lo, batch_end=hi)
+                for lo, hi in zip(cuts[:-1], cuts[1:]))
+    assert rel_max(total, whole) <= 2e-6
 
 
 @pytest.mark.parametrize("prec", ["float64", "float32"])

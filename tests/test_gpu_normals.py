@@ -24,7 +24,9 @@ from tests.helpers import expect_success
 
 pytestmark = pytest.mark.gpu
 
-SHAPES = [(12, 1024), (1, 16), (4, 4), (6, 8), (7, 132), (13, 1001), (5, 3), (252, 4096)]
+SHAPES = [(12, 1024), (1, 16), (4, 4), (6, 8), (7, 132), (13, 1001), (5, 3), (252, 4096),
+          # short float32 layout (rows <= 3: adjacent columns share a block), ragged column counts
+          (1, 65536), (1, 1001), (2, 1000), (2, 7), (3, 4097), (3, 1)]
 
 
 def _device_matrix(rows, cols, dtype, seed, k):

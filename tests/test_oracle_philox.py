@@ -131,3 +131,59 @@ def test_stream_is_a_pure_function_of_seed_index_row_col(dtype) -> None:
     assert not np.array_equal(full, philox.normals_matrix(9, 40, dtype, seed=6, matrix_index=2))
     other = np.float64 if dtype == np.float32 else np.float32
     assert not np.allclose(full, philox.normals_matrix(9, 40, other, seed=5, matrix_index=2), atol=1e-3)
+
+
+# ---- short-matrix layout (float32, rows <= 3): adjacent columns share one block ---------------------
+@pytest.mark.parametrize("rows", [1, 2, 3])
+def test_short_layout_shares_one_block_between_adjacent_columns(rows) -> None:
+    """Element (i, j) of a float32 matrix with rows <= 3 is normal (j % G) * rows + i of the block with counter
+    (j // G, 0x40000000, k lo, k hi), G = 6 // rows — restated here from the block primitives."""
+    G = 6 // rows
+    assert philox.short_group(rows, np.float32) == G and philox.short_group(rows, np.float64) == 1
+    cols, seed, k = 45, 11, (1 << 33) + 5
+    z = philox.normals_matrix(rows, cols, np.float32, seed, k)
+    groups = np.arange((cols + G - 1) // G, dtype=np.uint32)
+    x = philox.philox4x32_10((groups, philox.F32_SHORT_BIT, k & 0xFFFFFFFF, k >> 32), (seed & 0xFFFFFFFF, seed >> 32))
+    radius, angle = philox.f32_fields(*x)
+    six = []
+    for p in range(3):
+        assert (radius[p] != 0).all()  # no refinement among these few blocks
+        r = np.sqrt(-2.0 * np.log(philox.uniform_21(radius[p])))
+        theta = 2.0 * np.pi * (philox.uniform_21(angle[p]) - 0.5)
+        six += [r * np.cos(theta), r * np.sin(theta)]
+    six = np.stack(six).astype(np.float32)  # [6, groups]
+    for j in range(cols):
+        for i in range(rows):
+            assert z[i, j] == six[(j % G) * rows + i, j // G], (i, j)
+    # rows 4 and 5 keep the general layout: the first rows of a 6-row matrix
+    for r45 in (4, 5):
+        assert np.array_equal(philox.normals_matrix(r45, cols, np.float32, seed, k), philox.normals_matrix(6, cols, np.float32, seed, k)[:r45])
+    # the short layout does not reuse the general layout's blocks
+    assert not np.array_equal(z[0], philox.normals_matrix(6, cols, np.float32, seed, k)[0])
+
+
+def test_short_layout_known_answers() -> None:
+    """Pinned values of the short layout (seed 42, matrix 3): any change of the layout shows up here."""
+    z1 = philox.normals_matrix(1, 8, np.float32, 42, 3)[0]
+    z2 = philox.normals_matrix(2, 4, np.float32, 42, 3)
+    z3 = philox.normals_matrix(3, 4, np.float32, 42, 3)
+    # one block serves columns 0..5 of the 1-row matrix, 0..2 of the 2-row one and 0..1 of the 3-row one
+    assert np.array_equal(z1[:6], z2[:, :3].T.ravel()) and np.array_equal(z1[:6], z3[:, :2].T.ravel())
+    np.testing.assert_allclose(z1[:4], [-0.35923433, -0.12542744, -0.11234973, 0.93997437], rtol=2e-7)
+
+
+@pytest.mark.parametrize("rows", [1, 2, 3])
+def test_short_layout_slices_statistics_and_c_port(rows) -> None:
+    from oracle import cport
+
+    cols = 60000
+    z = philox.normals_matrix(rows, cols, np.float32, 5, 2)
+    assert np.array_equal(z[:, 1001:40007], philox.normals_matrix(rows, cols, np.float32, 5, 2, col_begin=1001, col_end=40007))
+    assert np.array_equal(z, cport.normals(rows, cols, np.float32, 5, 2))
+    flat = z.astype(np.float64).ravel()
+    assert abs(flat.mean()) < 5 / np.sqrt(flat.size) and abs(flat.var() - 1) < 5 * np.sqrt(2 / flat.size)
+    # the six normals of a block are mutually uncorrelated: adjacent columns and rows
+    G = 6 // rows
+    blocks = z[:, : cols // G * G].reshape(rows, -1, G).transpose(1, 2, 0).reshape(-1, 6).astype(np.float64)
+    c = np.corrcoef(blocks.T)
+    assert np.max(np.abs(c - np.eye(6))) < 6 / np.sqrt(blocks.shape[0])
