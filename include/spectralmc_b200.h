@@ -252,9 +252,10 @@ int smc_cf_from_terminal_p2p(const smc_fused_args* args, const smc_p2p_group* gr
 /* Host-buffer convenience for the reference-facing call: copies `contracts_host`
  * (ideally pinned) to the device, runs smc_cf_fused, copies the [n_contracts, N] complex
  * result to `cf_host` and synchronises `stream`.  args->contracts is ignored.  The workspace
- * must be smc_cf_fused_host_workspace_bytes() (device memory).  When a host buffer is pinned
- * (cudaHostAlloc / cudaHostRegister) and at most 64 KiB, the kernels read / write it directly
- * through its device alias instead of a staging copy; pageable buffers always take the copies. */
+ * must be smc_cf_fused_host_workspace_bytes() (device memory).  When `cf_host` is pinned
+ * (cudaHostAlloc / cudaHostRegister) and at most 64 KiB, the finishing CTAs write it directly through
+ * its device alias instead of a staging copy + D2H; pageable buffers take the copy.  The contracts
+ * are always copied to the device (every CTA reads them). */
 size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* args);
 int smc_cf_fused_host(const smc_fused_args* args, const double* contracts_host, void* cf_host,
                       void* workspace, size_t workspace_bytes, void* stream);
@@ -326,7 +327,7 @@ int smc_cvnn_train_step(const smc_cvnn_net* net, void* params, void* grads, void
 /* Pipe-peak calibration microbenchmarks (FP32 FMA issue and MUFU/XU), used by bench.py to
  * state the compute roofline on the box it runs on: each runs `iters` dependent-chain
  * iterations per thread on a full grid and returns executed lane-operations in *ops.
- * kind: 0 = FFMA, 1 = MUFU.EX2, 2 = IMAD.WIDE.U32 + LOP3 (Philox-like mix). */
+ * kind: 0 = FFMA, 1 = MUFU.EX2, 2 = IMAD.WIDE.U32 + LOP3 (Philox-like mix), 3 = DFMA (the FP64 pipe). */
 int smc_pipe_calibrate(int kind, int64_t iters, double* ops, float* sink /* device, >= 1 */,
                        void* stream);
 

@@ -160,6 +160,21 @@ __global__ void __launch_bounds__(BLK) calib_mufu_kernel(int64_t iters, float* s
   if (s == 123.456f) sink[0] = s;
 }
 
+__global__ void __launch_bounds__(BLK) calib_dfma_kernel(int64_t iters, float* sink) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1.0 + 1e-3 * (threadIdx.x + k);
+  const double m = 0.999999, c = 1e-7;
+  for (int64_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 123.456) sink[0] = static_cast<float>(s);
+}
+
 __global__ void __launch_bounds__(BLK) calib_philox_kernel(int64_t iters, PhiloxKeys key, float* sink) {
   uint32_t acc = 0;
   const uint32_t col = blockIdx.x * BLK + threadIdx.x;
@@ -278,7 +293,7 @@ extern "C" int smc_normalize_rows(void* sims, int64_t rows, int64_t cols, int dt
 
 extern "C" int smc_pipe_calibrate(int kind, int64_t iters, double* ops, float* sink, void* stream) {
   clear_error();
-  SMC_REQUIRE(kind >= 0 && kind <= 2, "smc_pipe_calibrate: invalid kind %d", kind);
+  SMC_REQUIRE(kind >= 0 && kind <= 3, "smc_pipe_calibrate: invalid kind %d", kind);
   SMC_REQUIRE(iters > 0 && sink != nullptr && ops != nullptr, "smc_pipe_calibrate: bad argument");
   const int sms = sm_count();
   SMC_REQUIRE(sms > 0, "smc_pipe_calibrate: no CUDA device");
@@ -291,6 +306,9 @@ extern "C" int smc_pipe_calibrate(int kind, int64_t iters, double* ops, float* s
   } else if (kind == 1) {
     calib_mufu_kernel<<<grid, BLK, 0, st>>>(iters, sink);
     *ops = threads * static_cast<double>(iters) * 8.0;  // MUFU lane-ops
+  } else if (kind == 3) {
+    calib_dfma_kernel<<<grid, BLK, 0, st>>>(iters, sink);
+    *ops = threads * static_cast<double>(iters) * 8.0;  // DFMA lane-ops
   } else {
     calib_philox_kernel<<<grid, BLK, 0, st>>>(iters, make_philox_keys(42), sink);
     *ops = threads * static_cast<double>(iters);  // Philox blocks

@@ -1662,11 +1662,10 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
   double* d_contracts = reinterpret_cast<double*>(base);
   void* d_out = base + align_up(cbytes);
   char* rest = base + align_up(cbytes) + align_up(obytes);
-  // Pinned host buffers are device-addressable under unified addressing.  For small batches the
-  // two staging copies are pure latency (48 bytes in, 1 KiB out at config c2), so the contract rows are
-  // read by the step kernel's CTAs, and the targets written by the finishing CTAs, straight through the
-  // mapped pointers; pageable memory and large batches take the staged copies.  (Every CTA reads a
-  // contract's 48 bytes when it first works on it, so the contracts take the alias only up to 4 KiB.)
+  // The contract rows are copied to the device (every CTA of the first wave reads them; through a host alias
+  // that was 36 000 PCIe transactions, +0.29 ms at config c2).  The targets are written ONCE, by the CTA that
+  // finishes a contract, so when the output buffer is pinned (device-addressable under unified addressing) and
+  // small, the kernel stores them straight into host memory instead of a staging copy + cudaMemcpyAsync.
   auto device_alias = [](const void* host) -> void* {
     cudaPointerAttributes attr{};
     if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
@@ -1675,16 +1674,11 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
     }
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
   };
-  constexpr size_t kZeroCopyIn = 4 << 10, kZeroCopyOut = 64 << 10;
-  void* c_alias = cbytes <= kZeroCopyIn ? device_alias(contracts_host) : nullptr;
+  constexpr size_t kZeroCopyOut = 64 << 10;
   void* o_alias = obytes <= kZeroCopyOut ? device_alias(cf_host) : nullptr;
   smc_fused_args b = *a;
-  if (c_alias) {
-    b.contracts = static_cast<const double*>(c_alias);
-  } else {
-    SMC_CUDA_OK(cudaMemcpyAsync(d_contracts, contracts_host, cbytes, cudaMemcpyHostToDevice, st));
-    b.contracts = d_contracts;
-  }
+  SMC_CUDA_OK(cudaMemcpyAsync(d_contracts, contracts_host, cbytes, cudaMemcpyHostToDevice, st));
+  b.contracts = d_contracts;
   if (int e = smc_cf_fused(&b, o_alias ? o_alias : d_out, rest, ws_bytes - align_up(cbytes) - align_up(obytes), stream)) return e;
   if (!o_alias) SMC_CUDA_OK(cudaMemcpyAsync(cf_host, d_out, obytes, cudaMemcpyDeviceToHost, st));
   SMC_CUDA_OK(cudaStreamSynchronize(st));
