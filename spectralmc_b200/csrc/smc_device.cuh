@@ -269,6 +269,7 @@ static __constant__ double kCosCoef[6] = {4.16666666666666019037e-02,  -1.388888
 static __constant__ double kLogCoef[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                           2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                           1.479819860511658591e-01};
+static __constant__ double kLn2 = 6.93147180559945286227e-01;
 static __constant__ double kLogMisc[4] = {6.93147180369123816490e-01 /* ln2 hi */, 1.90821492927058770002e-10 /* ln2 lo */,
                                           3.14159265358979311600e+00 /* pi hi */, 1.22464679914735317723e-16 /* pi lo */};
 
@@ -277,6 +278,15 @@ static __constant__ double kLogMisc[4] = {6.93147180369123816490e-01 /* ln2 hi *
 // 2^-22) and FP64 Newton steps.  The compiler's general-purpose sequences carry a range test, a branch
 // and an out-of-line slow path per call (12 of the 113 non-FP64 issue slots of the float64 loop);
 // the results here are within 1 ulp (tests/test_gpu_normals.py holds the stream to 1e-13).
+#ifndef SMC_F64_LEAN
+#define SMC_F64_LEAN 1  // 1: the float64 Box-Muller without the last-bit corrections below (50 instead of 59 FP64 instructions per pair)
+#endif
+// SMC_F64_LEAN drops four refinements whose effect is below 2 ulp of the result — far inside the 1e-13
+// the float64 stream is held to (tests/test_gpu_normals.py) and the 1e-12 of the CF parity:
+//   the residual correction of the quotient (q = a r with r good to 2^-66 is within 1 ulp),
+//   the residual correction of the square root (g = x y, y good to 2^-66),
+//   the split (hi, lo) accumulation of k ln 2 in the logarithm (one FMA: |k| <= 52, error < 1 ulp of the result),
+//   the second word of pi in the angle (|r| <= 1/4: absolute error 2^-55).
 __device__ __forceinline__ double div_pos_f64(double a, double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
@@ -284,7 +294,11 @@ __device__ __forceinline__ double div_pos_f64(double a, double d) {
   e = fma(e, e, e);                       // e + e^2
   r = fma(r, e, r);                       // r (1 + e + e^2): relative error 2^-66
   const double q = a * r;
+#if SMC_F64_LEAN
+  return q;
+#else
   return fma(fma(-d, q, a), r, q);        // one residual correction
+#endif
 }
 __device__ __forceinline__ double sqrt_pos_f64(double x) {
   double y;
@@ -292,7 +306,11 @@ __device__ __forceinline__ double sqrt_pos_f64(double x) {
   const double e = fma(-x * y, y, 1.0);            // 1 - x y^2
   y = fma(y * e, fma(e, 0.375, 0.5), y);           // y (1 + e/2 + 3 e^2 / 8)
   const double g = x * y;
+#if SMC_F64_LEAN
+  return g;
+#else
   return fma(fma(-g, g, x), 0.5 * y, g);           // g + (x - g^2) / (2 g)
+#endif
 }
 
 static __constant__ double kLogMisc2[2] = {2.0, 0x1p-52};  // angle / pi = 2 w + 2^-52 with constant-bank operands
@@ -313,14 +331,22 @@ __device__ __forceinline__ double log_unit_interval(double u) {
   const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
   const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
   const double R = t1 + t2, hfsq = 0.5 * f * f, dk = static_cast<double>(k);
+#if SMC_F64_LEAN
+  return fma(dk, kLn2, f - fma(-s, hfsq + R, hfsq));  // k ln 2 + (f - (hfsq - s (hfsq + R)))
+#else
   return dk * kLogMisc[0] - ((hfsq - fma(s, hfsq + R, dk * kLogMisc[1])) - f);
+#endif
 }
 
 // sin(pi t), cos(pi t) for |t| <= 1
 __device__ __forceinline__ void sincospi_unit(double t, double& sn, double& cs) {
   const double n = rint(2.0 * t);             // quadrant, in {-2 .. 2}
   const double r = fma(n, -0.5, t);           // exact, |r| <= 1/4
+#if SMC_F64_LEAN
+  const double x = r * kLogMisc[2];                        // pi r
+#else
   const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);  // pi r, two-term pi
+#endif
   const double z = x * x;
   const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
   const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);
@@ -340,7 +366,11 @@ __device__ __forceinline__ void sincospi_unit(double t, double& sn, double& cs) 
 __device__ __forceinline__ void sincospi_unit_terms(double t, double& c_term, double& s_term) {
   const double n = rint(2.0 * t);
   const double r = fma(n, -0.5, t);
+#if SMC_F64_LEAN
+  const double x = r * kLogMisc[2];
+#else
   const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);
+#endif
   const double z = x * x;
   const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
   const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu: a few launches of one hot-path kernel at BASELINE config c2 size.
 
-    python tools/prof_fused.py fused|fused_stepwise|fused_f64|normals|inplace|terminal [reps]
+    python tools/prof_fused.py fused|fused_stepwise|fused_f64|fused_c3|normals|inplace|terminal [reps]
 """
 import os
 import sys
@@ -16,7 +16,16 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 dev = torch.device("cuda", 0)
 CANON = (100.0, 100.0, 1.0, 0.05, 0.0, 0.2)
 T, N = 252, 128
-if what.startswith("fused"):
+if what == "fused_c3":  # trainer-test size: 1024 contracts, one timestep (short-path grouped layout)
+    import numpy as np
+    rows = np.tile(np.asarray(CANON), (1024, 1)); rows[:, 1] = np.linspace(80, 120, 1024)
+    contracts = torch.tensor(rows, dtype=torch.float64, device=dev)
+    for i in range(reps):
+        args = _cabi.make_fused_args(contracts, 1024, 1, 16, 4096, torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 7, i * 1024)
+        out = _cabi.cf_fused(args, dev, torch.float32)
+    torch.cuda.synchronize()
+    print(what, out[0, 0].item())
+elif what.startswith("fused"):
     dtype = torch.float64 if what.endswith("f64") else torch.float32
     B = 8192 if dtype == torch.float64 else 65536
     scheme = _cabi.SMC_LOG_EULER_STEPWISE if "stepwise" in what else _cabi.SMC_SIMPLE_EULER if "simple" in what else _cabi.SMC_LOG_EULER
