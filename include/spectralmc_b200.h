@@ -324,6 +324,23 @@ int smc_cvnn_train_step(const smc_cvnn_net* net, void* params, void* grads, void
                         const void* in_i, const void* targets, int64_t rows, double* loss,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Audit of the float32 normal stream on the device, with no matrix in HBM (the stream is this library's own
+ * specification, oracle/philox.py, so the library ships the means to test it at 2^33 draws and beyond;
+ * tests/test_gpu_stream_battery.py).  Block b of the audit is the Philox block of (column b mod cols, row group
+ * b div cols) of matrix `matrix_index`.
+ *   radius_hist / angle_hist   device uint32[2^21] each, ZEROED by the caller: counts of the 21-bit fields
+ *   tails4                     device uint64[4], zeroed: normals with |z| > 4, 5, 5.5, 6 (refined entries included)
+ *   power_sums4                device double[4], zeroed: sum z, z^2, z^3, z^4 over the 6 * n_blocks normals
+ * smc_diag_stream_lags_f32: sums7 (device double[7], zeroed) receives sum_i z[i,j] z[i-lag,j] for lag = 1..6 over
+ * all columns (rows a multiple of 6: products within AND across the 6-row blocks) and, in sums7[6], the products of
+ * horizontally adjacent entries z[i,j] z[i,j+1] (pairs inside one warp of 32 columns). */
+int smc_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols,
+                               uint32_t* radius_hist, uint32_t* angle_hist, uint64_t* tails4, double* power_sums4,
+                               void* stream);
+int smc_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7,
+                             void* stream);
+
 /* Pipe-peak calibration microbenchmarks (FP32 FMA issue and MUFU/XU), used by bench.py to
  * state the compute roofline on the box it runs on: each runs `iters` dependent-chain
  * iterations per thread on a full grid and returns executed lane-operations in *ops.

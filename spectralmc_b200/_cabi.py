@@ -35,7 +35,7 @@ EXPORTS = (
     "smc_cvnn_workspace_bytes smc_cvnn_output_width smc_cvnn_forward smc_cvnn_loss_backward smc_adam_step "
     "smc_cvnn_train_step "
     "smc_p2p_buffer_bytes smc_p2p_alloc smc_p2p_open smc_p2p_close smc_p2p_free smc_cf_fused_p2p "
-    "smc_p2p_allreduce_sum_f64 smc_cf_from_terminal_p2p smc_cf_fused_p2p_check smc_p2p_status smc_cf_fused_plan"
+    "smc_p2p_allreduce_sum_f64 smc_cf_from_terminal_p2p smc_cf_fused_p2p_check smc_p2p_status smc_cf_fused_plan smc_diag_stream_fields_f32 smc_diag_stream_lags_f32"
 ).split()
 
 SMC_LAYER_LINEAR, SMC_LAYER_MODRELU, SMC_LAYER_ZRELU = 0, 1, 2
@@ -162,6 +162,8 @@ def _load() -> ctypes.CDLL:
     lib.smc_p2p_free.argtypes = [c_void_p]
     lib.smc_cf_fused_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_p2p_allreduce_sum_f64.argtypes = [c_void_p, c_int64, POINTER(P2PGroup), c_void_p]
+    lib.smc_diag_stream_fields_f32.argtypes = [c_uint64, c_uint64, c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.smc_diag_stream_lags_f32.argtypes = [c_uint64, c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p]
     lib.smc_cf_fused_plan.argtypes = [POINTER(FusedArgs), POINTER(c_int64), c_int]
     lib.smc_cf_fused_p2p_check.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_size_t]
     lib.smc_p2p_status.argtypes = [POINTER(P2PGroup), POINTER(ctypes.c_uint32), c_void_p]
@@ -568,6 +570,24 @@ def cvnn_train_step(net: CvnnNet, params: torch.Tensor, grads: torch.Tensor, exp
             workspace.data_ptr(), workspace.numel(), _stream(),
         )
     )
+
+
+# --------------------------------------------------------------------------- stream audit
+def diag_stream_fields(seed: int, matrix_index: int, n_blocks: int, cols: int, device: torch.device) -> dict:
+    """Field histograms, tail counts and power sums of ``6 * n_blocks`` float32-stream normals (no matrix in HBM)."""
+    radius = torch.zeros(1 << 21, dtype=torch.int32, device=device)
+    angle = torch.zeros(1 << 21, dtype=torch.int32, device=device)
+    tails = torch.zeros(4, dtype=torch.int64, device=device)
+    sums = torch.zeros(4, dtype=torch.float64, device=device)
+    check(LIB.smc_diag_stream_fields_f32(seed, matrix_index, n_blocks, cols, radius.data_ptr(), angle.data_ptr(), tails.data_ptr(),
+                                         sums.data_ptr(), _stream()))
+    return {"radius_hist": radius, "angle_hist": angle, "tails": tails, "power_sums": sums}
+
+
+def diag_stream_lags(seed: int, matrix_index: int, cols: int, rows: int, device: torch.device) -> torch.Tensor:
+    sums = torch.zeros(7, dtype=torch.float64, device=device)
+    check(LIB.smc_diag_stream_lags_f32(seed, matrix_index, cols, rows, sums.data_ptr(), _stream()))
+    return sums
 
 
 # --------------------------------------------------------------------------- peer-memory exchange

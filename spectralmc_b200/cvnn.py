@@ -321,6 +321,10 @@ class FusedCVNN:
     exp_avg_sq = property(lambda self: self.adam.exp_avg_sq)
     step = property(lambda self: self.adam.step)
 
+    def complex_macs(self, rows: int) -> int:
+        """Complex multiply-adds of one forward pass over ``rows`` inputs (the step does three GEMMs per layer)."""
+        return rows * sum(layer[1] * layer[2] for layer in self.layers if layer[0] == "linear")
+
     @property
     def hyper(self) -> "_cabi.AdamArgs":
         return self.adam.hyper

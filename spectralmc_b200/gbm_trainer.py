@@ -71,6 +71,11 @@ def _split_inputs(rows: np.ndarray | Sequence[BlackScholes.Inputs], *, dtype: to
     return real, torch.zeros_like(real)
 
 
+# complex multiply-adds per training step (rows x sum of in x out over the linear layers) above which the graphed torch
+# route is faster than the C-ABI step on a B200: 0.6x at 8.2e8, 1.04x at 1.2e9 and 2.7e9, 1.44x at 9.7e9
+FUSED_STEP_MAX_MACS = 1_000_000_000
+
+
 @dataclass(frozen=True)
 class TrainingConfig:
     """Training hyper-parameters (reference :252-258); validate with ``build_training_config``."""
@@ -200,6 +205,9 @@ class GbmCVNNPricer:
         if fused_step and not supported:
             raise ValueError("fused_step=True needs a ComplexSequential of ComplexLinear / modReLU / zReLU")
         self._use_fused = supported if fused_step is None else fused_step
+        # fused_step=None: per batch size, the C-ABI step below FUSED_STEP_MAX_MACS complex multiply-adds per step and
+        # torch autograd (cuBLAS SGEMM) + smc_adam_step above it — measured crossover, profiles/r2_cvnn_widths.md
+        self._route_by_size = fused_step is None
         self._use_graph = cuda_graph
         self._fused: FusedCVNN | None = None
         self._graphs: dict[int, _StepGraph] = {}
@@ -273,6 +281,17 @@ class GbmCVNNPricer:
         if not self._use_graph:
             real_in = contracts.to(self._dtype)
             loss_slot.copy_(fused.train_step(real_in, torch.zeros_like(real_in), targets))
+            return
+        if self._route_by_size and fused.complex_macs(rows) > FUSED_STEP_MAX_MACS:
+            # wide network x large batch: the SIMT complex GEMM of the C-ABI step (~25 TFLOP/s) falls behind cuBLAS; the
+            # same flat parameter / gradient / Adam buffers are stepped by the graphed torch route instead
+            tg = self._torch_graphs.get(rows)
+            if tg is None:
+                tg = self._torch_graphs[rows] = _TorchStepGraph(self._cvnn, fused.adam, rows, contracts.shape[1], targets.shape[1], self._dtype)
+            tg.real_in.copy_(contracts)
+            tg.targets.copy_(targets)
+            tg.graph.replay()
+            loss_slot.copy_(tg.loss)
             return
         g = self._graphs.get(rows)
         if g is None:

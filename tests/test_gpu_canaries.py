@@ -113,3 +113,88 @@ def test_cf_kernels_stay_inside_their_buffers(dtype, code, b, n) -> None:
         spec = Guarded(b * n * 2 * es)
         _cabi.check(_cabi.LIB.smc_fft_rows(mat.ptr, b, n, code, spec.ptr, None))
         spec.check("fft_rows out")
+
+
+# ---- peer exchange on ONE device: two "ranks" whose exchange buffers are guarded torch allocations --------------
+def _group(rank, world, bufs, cap, n, epoch, timeout_ms=0):
+    g = _cabi.P2PGroup()
+    g.rank, g.world = rank, world
+    for q, b in enumerate(bufs):
+        g.buffers[q] = b.ptr
+    g.capacity_contracts, g.network_size, g.epoch, g.timeout_ms = cap, n, epoch, timeout_ms
+    return g
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("N,B,norm", [(64, 40, _cabi.SMC_RAW), (48, 21, _cabi.SMC_RAW), (16, 33, _cabi.SMC_NORMALIZE)])
+def test_peer_exchange_stays_inside_its_buffers(dtype, N, B, norm) -> None:
+    """The exchange layout (data slots, per-contract flags, small all-reduce region, status word) addressed by both
+    ranks of a 2-rank group, each rank on its own stream of the same device: guard bands around BOTH exchange
+    buffers, the outputs and the workspaces stay intact, and the result equals the unsharded call — three epochs,
+    so both slot parities are reused."""
+    contracts = torch.tensor(ROWS, dtype=torch.float64, device="cuda")
+    C, T, world = len(ROWS), 9, 2
+    esz = 8 if dtype == torch.float32 else 16
+    nbytes = int(_cabi.LIB.smc_p2p_buffer_bytes(C, N, world))
+    bufs = [Guarded(nbytes) for _ in range(world)]
+    for b in bufs:
+        b.raw[GUARD : GUARD + b.nbytes].zero_()  # epochs start at 1: a zeroed flag is "not yet"
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    cuts = [0, B // 3, B]
+    whole = _cabi.cf_fused(_cabi.make_fused_args(contracts, C, T, N, B, dtype, 0, norm, 42, 3), contracts.device, dtype)
+    torch.cuda.synchronize()
+    for epoch in (1, 2, 3):
+        outs, keep = [], []
+        for rank in range(world):
+            a = _cabi.make_fused_args(contracts, C, T, N, B, dtype, 0, norm, 42, 3, batch_begin=cuts[rank], batch_end=cuts[rank + 1])
+            g = _group(rank, world, bufs, C, N, epoch)
+            out = Guarded(C * N * esz)
+            st = streams[rank].cuda_stream
+            if norm == _cabi.SMC_RAW:
+                need = int(_cabi.LIB.smc_cf_fused_workspace_bytes(ctypes.byref(a)))
+                ws = Guarded(need)
+                _cabi.check(_cabi.LIB.smc_cf_fused_p2p(ctypes.byref(a), ctypes.byref(g), out.ptr, ws.ptr, need, st))
+                keep += [ws]
+            else:
+                rows_local = cuts[rank + 1] - cuts[rank]
+                term, tsum = Guarded(C * rows_local * N * (esz // 2)), Guarded(C * 8)
+                need_a = int(_cabi.LIB.smc_fused_terminal_workspace_bytes(ctypes.byref(a)))
+                need_b = int(_cabi.LIB.smc_cf_from_terminal_workspace_bytes(ctypes.byref(a)))
+                ws_a, ws_b = Guarded(need_a), Guarded(need_b)
+                _cabi.check(_cabi.LIB.smc_fused_terminal(ctypes.byref(a), term.ptr, tsum.ptr, ws_a.ptr, need_a, st))
+                _cabi.check(_cabi.LIB.smc_p2p_allreduce_sum_f64(tsum.ptr, C, ctypes.byref(g), st))
+                _cabi.check(_cabi.LIB.smc_cf_from_terminal_p2p(ctypes.byref(a), ctypes.byref(g), term.ptr, tsum.ptr, out.ptr, ws_b.ptr, need_b, st))
+                keep += [term, tsum, ws_a, ws_b]
+            outs.append(out)
+            keep.append(out)
+        torch.cuda.synchronize()
+        for i, k in enumerate(keep + bufs):
+            k.check(f"epoch {epoch} buffer {i}")
+        cdt = torch.complex64 if dtype == torch.float32 else torch.complex128
+        got = [o.view(cdt, (C, N)) for o in outs]
+        assert torch.equal(torch.view_as_real(got[0]), torch.view_as_real(got[1]))  # identical bits on both ranks
+        tol = 2e-6 if dtype == torch.float32 else 1e-12
+        assert float((got[0] - whole).abs().max() / whole.abs().max()) <= tol
+
+
+def test_peer_that_never_arrives_is_reported_not_trapped() -> None:
+    """A wait for a peer is bounded in TIME: the targets come back NaN, the status word names the epoch, and the
+    CUDA context survives (the next call works) — no device trap that would take every rank down in turn."""
+    contracts = torch.tensor(ROWS, dtype=torch.float64, device="cuda")
+    C, T, N, B = len(ROWS), 6, 32, 16
+    nbytes = int(_cabi.LIB.smc_p2p_buffer_bytes(C, N, 2))
+    bufs = [Guarded(nbytes) for _ in range(2)]
+    for b in bufs:
+        b.raw[GUARD : GUARD + b.nbytes].zero_()
+    a = _cabi.make_fused_args(contracts, C, T, N, B, torch.float32, 0, _cabi.SMC_RAW, 42, 0, batch_begin=0, batch_end=B // 2)
+    g = _group(0, 2, bufs, C, N, 7, timeout_ms=50)  # rank 1 never calls
+    out = _cabi.cf_fused_p2p(a, g, contracts.device, torch.float32)
+    torch.cuda.synchronize()  # no sticky error
+    assert bool(torch.isnan(torch.view_as_real(out)).all())
+    status = ctypes.c_uint32(0)
+    _cabi.check(_cabi.LIB.smc_p2p_status(ctypes.byref(g), ctypes.byref(status), None))
+    assert status.value == 7
+    for b in bufs:
+        b.check("exchange buffer after a timeout")
+    again = _cabi.cf_fused(_cabi.make_fused_args(contracts, C, T, N, B, torch.float32, 0, _cabi.SMC_RAW, 42, 0), contracts.device, torch.float32)
+    assert bool(torch.isfinite(torch.view_as_real(again)).all())

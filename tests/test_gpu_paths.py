@@ -51,6 +51,56 @@ def test_path_kernel_inplace(golden) -> None:
     assert rel_elem(got, _kernel_only_reference(g)) <= _tol(got.dtype), g["name"]
 
 
+def test_launch_object_accepts_what_the_reference_passes(golden) -> None:
+    """The reference launches with ``cuda.as_cuda_array(sims)`` and a Numba stream (gbm.py:413-426,
+    effects/interpreter.py:634-654): a Numba device array (``__cuda_array_interface__``) and a ``numba.cuda.stream()``
+    must go through the same launch object, zero-copy and in place."""
+    numba_cuda = pytest.importorskip("numba.cuda")
+    g = golden
+    X0, K, T, r, d, v = (float(x) for x in g["contract"])
+    rows = int(g["timesteps"])
+    torch.cuda.synchronize()
+    io = numba_cuda.to_device(g["normals"].copy())
+    stream = numba_cuda.stream()
+    SimulateBlackScholes[1, int(g["threads_per_block"]), stream](io, rows, T / rows, X0, r, d, v, str(g["scheme"]) == "log_euler")
+    stream.synchronize()
+    got = io.copy_to_host()
+    if str(g["normalization"]) == "raw_paths":
+        assert rel_elem(got, g["sims"]) <= _tol(got.dtype), g["name"]
+    assert rel_elem(got, _kernel_only_reference(g)) <= _tol(got.dtype), g["name"]
+
+
+def test_launch_object_accepts_dlpack_and_raw_stream_handles() -> None:
+    z = torch.randn(5, 64, device="cuda", dtype=torch.float64)
+    want = z.clone()
+    SimulateBlackScholes[1, 256](want, 5, 0.2, 100.0, 0.05, 0.0, 0.2, True)
+
+    class OnlyDLPack:  # a foreign array that exports DLPack and nothing else
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, **kw):
+            return self._t.__dlpack__(**kw)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    a, b = z.clone(), z.clone()
+    SimulateBlackScholes[1, 256, torch.cuda.current_stream().cuda_stream](OnlyDLPack(a), 5, 0.2, 100.0, 0.05, 0.0, 0.2, True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    SimulateBlackScholes[1, 256, side](b, 5, 0.2, 100.0, 0.05, 0.0, 0.2, True)
+    side.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(a, want) and torch.equal(b, want)
+    with pytest.raises(ValueError):  # a host array (NumPy exports DLPack too) is refused loudly: there is no CPU path
+        SimulateBlackScholes[1, 256](z.cpu().numpy(), 5, 0.2, 100.0, 0.05, 0.0, 0.2, True)
+    with pytest.raises(TypeError):
+        SimulateBlackScholes[1, 256]([[1.0, 2.0]], 1, 0.2, 100.0, 0.05, 0.0, 0.2, True)
+    with pytest.raises(ValueError):
+        SimulateBlackScholes[1, 256](z.t(), 64, 0.2, 100.0, 0.05, 0.0, 0.2, True)  # not C-contiguous
+
+
 def test_terminal_only_kernel(golden) -> None:
     g = golden
     X0, K, T, r, d, v = (float(x) for x in g["contract"])

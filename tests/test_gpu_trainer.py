@@ -208,3 +208,28 @@ def test_full_stack_normalize_train_snapshot_reload_predict() -> None:
     expect_success(trainer.train(_tc(1, batch_size=8)))
     expect_success(reloaded.train(_tc(1, batch_size=8)))
     assert _max_param_diff(trainer, reloaded) == 0.0
+
+
+def test_wide_steps_take_the_graphed_torch_route_on_the_same_buffers(monkeypatch) -> None:
+    """fused_step=None routes per batch size: below FUSED_STEP_MAX_MACS the C-ABI step, above it torch autograd +
+    smc_adam_step (profiles/r2_cvnn_widths.md) — on the SAME flat parameter / Adam buffers, so a run may mix batch
+    sizes.  With the threshold forced to zero every step takes the torch route and must track the C-ABI route."""
+    import spectralmc_b200.gbm_trainer as gt
+
+    a = _pricer(Precision.float32, seed=5, N=16, B=2**8)
+    b = _pricer(Precision.float32, seed=5, N=16, B=2**8)
+    monkeypatch.setattr(gt, "FUSED_STEP_MAX_MACS", 0)
+    la = expect_success(a.train(_tc(6, batch_size=16))).losses
+    assert a._torch_graphs and not a._graphs  # every step went through the torch graph
+    monkeypatch.setattr(gt, "FUSED_STEP_MAX_MACS", 10**18)
+    lb = expect_success(b.train(_tc(6, batch_size=16))).losses
+    assert b._graphs and not b._torch_graphs
+    assert np.allclose(la, lb, rtol=2e-4)
+    assert _max_param_diff(a, b) <= 2e-4
+    # mixing the routes on one trainer: the optimiser state lives in one place
+    monkeypatch.setattr(gt, "FUSED_STEP_MAX_MACS", 0)
+    expect_success(b.train(_tc(2, batch_size=16)))
+    expect_success(a.train(_tc(2, batch_size=16)))
+    assert _max_param_diff(a, b) <= 5e-4
+    snap = expect_success(a.snapshot())
+    assert snap.global_step == 8 and snap.optimizer_state is not None

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/../spectralmc_b200/csrc"
 name=$1; shift
 out=../../tools/tune/lib_${name}.so
 tmp=$(mktemp -d)
-for f in smc_api smc_normals smc_paths smc_cf smc_rowfft smc_cvnn; do
+for f in smc_api smc_normals smc_paths smc_cf smc_rowfft smc_cvnn smc_diag; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v -I../../include "$@" -c $f.cu -o $tmp/$f.o 2> $tmp/$f.log &
 done
 wait
