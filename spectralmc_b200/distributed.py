@@ -52,6 +52,20 @@ def shard_batches(batches_total: int, world_size: int, rank: int) -> BatchShard:
     return BatchShard(rank, world_size, batches_total, begin, begin + base + (1 if rank < extra else 0))
 
 
+def shard_contracts(n_contracts: int, world_size: int, rank: int) -> tuple[int, int]:
+    """Contiguous, near-equal split of a contract batch: ``[begin, end)`` of ``rank`` (possibly empty)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, extra = divmod(n_contracts, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+# below this many paths per contract and rank a batch-row shard no longer fills a GPU (c3 at the trainer-test size
+# leaves each of 8 ranks 512 rows x 16 columns per contract) and whole contracts are dealt out instead
+CONTRACT_SHARD_MAX_PATHS = 100_000
+
+
 class DeviceOps(Protocol):
     def cf_fused(self, args: _cabi.FusedArgs) -> torch.Tensor: ...
     def fused_terminal(self, args: _cabi.FusedArgs) -> tuple[torch.Tensor, torch.Tensor]: ...
@@ -184,6 +198,38 @@ class PeerExchange:
             _cabi.check(_cabi.LIB.smc_p2p_free(own))
 
 
+def _contract_sharded(engine: BlackScholes, contracts: torch.Tensor, world: int, rank: int, group, ops: DeviceOps | None) -> torch.Tensor:
+    """Whole contracts dealt out to the ranks; contract c still consumes matrix ``skip + c`` of the stream."""
+    if ops is None:
+        contracts = engine.contract_rows(contracts)
+    else:
+        if contracts.dim() != 2 or contracts.shape[1] != 6:
+            raise ValueError(f"contracts must have shape [C, 6]; got {tuple(contracts.shape)}")
+        contracts = contracts.to(torch.float64).contiguous()
+    n, width = contracts.shape[0], engine._sp.network_size
+    begin, end = shard_contracts(n, world, rank)
+    per = -(-n // world)  # slices are padded to one length: all_gather_into_tensor wants equal parts
+    cdtype = _cabi.complex_dtype(engine._dtype)
+    device = contracts.device if ops is not None else engine._device
+    mine = torch.zeros((per, width), dtype=cdtype, device=device)
+    if end > begin:
+        part = contracts[begin:end].contiguous()
+        args = engine.fused_args(part, end - begin, matrix_offset=begin)
+        if ops is None:
+            out = _cabi.cf_fused(args, engine._device, engine._dtype)  # RAW or NORMALIZE: a contract's mean is local
+        elif engine._cfg.normalization is ForwardNormalization.RAW:
+            out = ops.cf_fused(args)
+        else:
+            terminal, tsum = ops.fused_terminal(args)
+            out = ops.cf_from_terminal(args, terminal, tsum)
+        mine[: end - begin] = out.to(cdtype)
+    gathered = torch.empty((world * per, width), dtype=cdtype, device=device)  # rank q's slice at rows [q per, (q + 1) per)
+    dist.all_gather_into_tensor(torch.view_as_real(gathered), torch.view_as_real(mine), group=group)
+    engine.consume(n)
+    pieces = [gathered[q * per : q * per + shard_contracts(n, world, q)[1] - shard_contracts(n, world, q)[0]] for q in range(world)]
+    return torch.cat(pieces, dim=0)
+
+
 def _all_reduce_sum(t: torch.Tensor, group) -> None:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM, group=group)
@@ -197,11 +243,27 @@ def sharded_cf_targets(
     ops: DeviceOps | None = None,
     max_staging_bytes: int = 8 << 30,
     exchange: PeerExchange | None = None,
+    shard: str = "batches",
 ) -> torch.Tensor:
-    """CF targets ``[C, N]`` of ``contracts`` (``[C, 6]`` float64 on the engine's device), with the
-    batch dimension sharded over the ranks of ``group``.  Every rank returns the full result."""
+    """CF targets ``[C, N]`` of ``contracts`` (``[C, 6]`` float64 on the engine's device) computed by all ranks of
+    ``group``; every rank returns the full result.
+
+    ``shard="batches"`` (default): every rank simulates batch rows ``[begin, end)`` of ALL contracts and the partial
+    sums are exchanged (one all-reduce, or the exchange fused into the kernels over peer memory).
+    ``shard="contracts"``: the alternative of SURVEY.md §8e for small path counts — every rank simulates ALL batch rows
+    of its contiguous slice of the contracts and one all-gather assembles ``[C, N]``; no reduction crosses ranks (so
+    NORMALIZE needs no second exchange) and the result is bit-identical to the single-GPU one.
+    ``shard="auto"``: contracts when a batch-row shard would leave a rank fewer than CONTRACT_SHARD_MAX_PATHS paths
+    per contract and there are at least as many contracts as ranks, else batches."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    if shard not in ("batches", "contracts", "auto"):
+        raise ValueError(f"shard must be 'batches', 'contracts' or 'auto'; got {shard!r}")
+    if shard == "auto":
+        per_rank_paths = engine._sp.total_paths() // max(world, 1)
+        shard = "contracts" if world > 1 and per_rank_paths < CONTRACT_SHARD_MAX_PATHS and contracts.shape[0] >= world else "batches"
+    if shard == "contracts" and world > 1:
+        return _contract_sharded(engine, contracts, world, rank, group, ops)
     if ops is None:
         contracts = engine.contract_rows(contracts)  # [C, 6] float64 contiguous on the engine's device, as cf_targets does
     else:  # a stand-in for the device calls (CPU tests) reads the rows where they are

@@ -376,8 +376,10 @@ class BlackScholes:
         batch_begin: int = 0,
         batch_end: int | None = None,
         scheme: int | None = None,
+        matrix_offset: int = 0,
     ) -> _cabi.FusedArgs:
-        """``smc_fused_args`` for the next ``n_contracts`` matrices of this engine's stream."""
+        """``smc_fused_args`` for ``n_contracts`` matrices of this engine's stream, starting ``matrix_offset`` after the
+        next unconsumed one (a rank that handles contracts [c0, c1) of a batch passes ``matrix_offset=c0``)."""
         return _cabi.make_fused_args(
             contracts_dev,
             n_contracts,
@@ -388,7 +390,7 @@ class BlackScholes:
             _SCHEME_CODE[self._cfg.path_scheme] if scheme is None else scheme,
             _NORM_CODE[self._cfg.normalization],
             self._sp.mc_seed,
-            self._served,
+            self._served + matrix_offset,
             batch_begin,
             batch_end,
         )

@@ -250,7 +250,8 @@ class GbmCVNNPricer:
                     self._exchange.close()
                 self._exchange = PeerExchange(int(dev.shape[0]), self._sp.network_size, group=self._group)  # collective set-up
             try:
-                return Success(sharded_cf_targets(self._engine, dev, group=self._group, exchange=self._exchange))
+                # "auto": whole contracts per rank + one all-gather when a batch-row shard would be too small to fill a GPU
+                return Success(sharded_cf_targets(self._engine, dev, group=self._group, exchange=self._exchange, shard="auto"))
             except _cabi.SmcError as exc:  # same error ADT as the single-GPU path (BlackScholes.cf_targets)
                 return Failure(DeviceKernelFailed(status=exc.code, message=exc.message))
         return self._engine.cf_targets(dev)

@@ -88,12 +88,12 @@ def _engine(norm: ForwardNormalization) -> BlackScholes:
     return BlackScholes(make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=norm))
 
 
-def _worker(rank: int, world: int, port: int, norm_value: str, chunk_bytes: int, queue) -> None:
+def _worker(rank: int, world: int, port: int, norm_value: str, chunk_bytes: int, queue, shard: str = "batches") -> None:
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         engine = _engine(ForwardNormalization(norm_value))
         contracts = torch.tensor(ROWS, dtype=torch.float64)
-        out = sharded_cf_targets(engine, contracts, ops=OracleOps(), max_staging_bytes=chunk_bytes)
+        out = sharded_cf_targets(engine, contracts, ops=OracleOps(), max_staging_bytes=chunk_bytes, shard=shard)
         queue.put((rank, out.numpy(), engine.snapshot().unwrap().sim_params.skip))
     finally:
         dist.destroy_process_group()
@@ -106,19 +106,24 @@ def _free_port() -> int:
 
 
 @pytest.mark.parametrize(
-    "world,norm,chunk_bytes",
+    "world,norm,chunk_bytes,shard",
     [
-        (2, ForwardNormalization.RAW, 8 << 30),
-        (2, ForwardNormalization.NORMALIZE, 8 << 30),
-        (2, ForwardNormalization.NORMALIZE, 1),  # 1 byte: one contract per NORMALIZE chunk
-        (3, ForwardNormalization.NORMALIZE, 8 << 30),
+        (2, ForwardNormalization.RAW, 8 << 30, "batches"),
+        (2, ForwardNormalization.NORMALIZE, 8 << 30, "batches"),
+        (2, ForwardNormalization.NORMALIZE, 1, "batches"),  # 1 byte: one contract per NORMALIZE chunk
+        (3, ForwardNormalization.NORMALIZE, 8 << 30, "batches"),
+        # whole contracts dealt out + one all-gather (the alternative for small path counts); with more
+        # ranks than contracts divide evenly, slices are ragged and padded; "auto" picks contracts at this size
+        (2, ForwardNormalization.RAW, 8 << 30, "contracts"),
+        (2, ForwardNormalization.NORMALIZE, 8 << 30, "contracts"),
+        (3, ForwardNormalization.NORMALIZE, 8 << 30, "auto"),
     ],
 )
-def test_sharded_targets_equal_the_unsharded_result(world, norm, chunk_bytes) -> None:
+def test_sharded_targets_equal_the_unsharded_result(world, norm, chunk_bytes, shard) -> None:
     ctx = mp.get_context("spawn")
     queue = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, norm.value, chunk_bytes, queue)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, norm.value, chunk_bytes, queue, shard)) for r in range(world)]
     for p in procs:
         p.start()
     results = [queue.get(timeout=120) for _ in range(world)]

@@ -242,7 +242,7 @@ def test_fused_prices_match_black76(precision, T) -> None:
     eps = 1e-4 if precision is Precision.float32 else 1e-8
     z = np.where(se > 0, np.abs(mean - analytic) / np.where(se > 0, se, 1), np.where(np.abs(mean - analytic) <= eps * np.maximum(analytic, 1), 0.0, 4.0))
     big = analytic >= 1.0
-    rmspe = float(np.sqrt(np.mean(((mean - analytic) / analytic)[big] ** 2)))
+    rmspe = float(np.sqrt(np.mean(((mean[big] - analytic[big]) / analytic[big]) ** 2)))
     assert float(np.mean(z > 3.0)) <= 0.05, np.sort(z)[-5:]
     assert rmspe <= 0.15
     assert expect_success(engine.snapshot()).sim_params.skip == 16 * 64

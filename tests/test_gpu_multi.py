@@ -180,3 +180,56 @@ def test_two_gpu_fused_peer_exchange_matches_nccl_and_single_gpu(prec, norm) -> 
             assert np.max(np.abs(f0[step] - n0[step])) <= tol * scale, (key, step)
         assert np.max(np.abs(f0[0] - w0)) <= tol * np.max(np.abs(w0)), key
         assert not np.array_equal(f0[0], f0[1])  # later calls consume later normal matrices
+
+
+def _contract_shard_worker(rank: int, world: int, port: int, norm: str, queue) -> None:
+    import torch.distributed as dist
+
+    from spectralmc_b200.distributed import sharded_cf_targets
+    from spectralmc_b200.effects import ForwardNormalization, PathScheme
+    from spectralmc_b200.gbm import BlackScholes
+    from spectralmc_b200.numerical import Precision
+    from tests.helpers import expect_success, make_black_scholes_config, make_simulation_params
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        # the reference's own test size: one timestep, 16 x 4096 paths per contract (tests/test_gbm_trainer.py:127-136)
+        sp = make_simulation_params(timesteps=1, network_size=16, batches_per_mc_run=4096, mc_seed=5, skip=7, dtype=Precision.float32)
+        cfg = make_black_scholes_config(sim_params=sp, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization(norm))
+        rows = np.tile(np.asarray(ROWS[0]), (37, 1))
+        rows[:, 1] = np.linspace(70.0, 130.0, 37)  # 37 contracts: ragged slices (19 + 18)
+        contracts = torch.tensor(rows, dtype=torch.float64, device="cuda")
+        engine = BlackScholes(cfg)
+        dealt = sharded_cf_targets(engine, contracts, shard="contracts")
+        auto = sharded_cf_targets(BlackScholes(cfg), contracts, shard="auto")  # picks contracts at this size
+        whole = expect_success(BlackScholes(cfg).cf_targets(contracts))
+        torch.cuda.synchronize()
+        queue.put((rank, dealt.cpu().numpy(), auto.cpu().numpy(), whole.cpu().numpy(), expect_success(engine.snapshot()).sim_params.skip))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("norm", ["raw_paths", "normalize_forwards"])
+def test_two_gpu_contract_sharding_is_bit_identical_to_one_gpu(norm) -> None:
+    """Whole contracts dealt out + one all-gather (the alternative for small path counts): no sum
+    crosses ranks, so every rank holds exactly the single-GPU bits, and the stream advances by all 37 matrices."""
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_contract_shard_worker, args=(r, 2, port, norm, queue)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [queue.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, dealt, auto, whole, skip in results:
+        assert np.array_equal(dealt, whole) and np.array_equal(auto, whole), rank
+        assert skip == 7 + 37

@@ -172,3 +172,35 @@ def test_registry_mirrors_the_reference_names() -> None:
     assert isinstance(reg.register_kernel("", print), Failure) and isinstance(reg.get_kernel("other"), Failure)
     reg.clear_tensors()
     assert not reg.has_tensor("z") and reg.has_kernel("mine")
+
+
+def test_import_level_drop_in_alias() -> None:
+    """``from spectralmc.gbm import ...`` resolves to this package after ``install_as_spectralmc()``; a real
+    installation would not be shadowed silently; out-of-scope modules stay unresolved."""
+    import importlib
+    import sys
+
+    import pytest
+
+    import spectralmc_b200.compat as compat
+
+    assert "spectralmc" not in sys.modules
+    names = compat.install_as_spectralmc()
+    try:
+        assert "spectralmc.gbm" in names and "spectralmc.effects.montecarlo" in names
+        gbm = importlib.import_module("spectralmc.gbm")
+        from spectralmc.async_normals import ConcurrentNormGenerator  # noqa: F401
+        from spectralmc.effects.montecarlo import ForwardNormalization as FN
+        from spectralmc.models.numerical import Precision as P
+        from spectralmc.sobol_sampler import SobolSampler  # noqa: F401
+
+        import spectralmc_b200
+
+        assert gbm.BlackScholes is spectralmc_b200.BlackScholes and gbm.SimulateBlackScholes is spectralmc_b200.SimulateBlackScholes
+        assert FN is spectralmc_b200.ForwardNormalization and P is spectralmc_b200.Precision
+        with pytest.raises(ImportError):
+            importlib.import_module("spectralmc.storage")  # out of scope: loudly absent
+        compat.install_as_spectralmc()  # idempotent over its own aliases
+    finally:
+        compat.uninstall()
+    assert "spectralmc" not in sys.modules and "spectralmc.gbm" not in sys.modules
