@@ -719,25 +719,36 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
                                                    int64_t row0, int64_t row1, double* __restrict__ dst, double* sm,
                                                    double* lanes /* shared, 256 G doubles */) {
   constexpr int G = 6 / T;
-  const int64_t p0 = row0 * p.n, p1 = row1 * p.n;  // the tile's global paths [p0, p1)
+  const int64_t p0 = row0 * p.n, p1 = row1 * p.n;  // the tile's global paths [p0, p1), p1 <= 2^32 - 1
   const int64_t g_first = p0 / G, g_end = (p1 + G - 1) / G;
+  // groups [g_in0, g_in1) lie wholly inside the tile and need no per-path range check; at most the first and the
+  // last group of a tile are cut by its boundary (a cut group is drawn by both tiles, each keeping its own lanes)
+  const uint32_t g_in0 = static_cast<uint32_t>((p0 + G - 1) / G), g_in1 = static_cast<uint32_t>(p1 / G);
   double acc[G];
 #pragma unroll
   for (int u = 0; u < G; ++u) acc[u] = 0.0;
-  for (int64_t g = g_first + threadIdx.x; g < g_end; g += CF_BLOCK) {
+  auto put_of = [&](const float (&z)[6], int u) {
+    float state = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
+#pragma unroll
+    for (int i = 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
+    const float val = SCHEME == SMC_LOG_EULER ? k.X0 * mufu_ex2(fmaf(k.lin1, state, k.lin0)) : state;
+    const float diff = k.K - val;
+    return k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
+  };
+  const uint32_t g_stop = static_cast<uint32_t>(g_end);  // g_end <= 2^32 / G + 1
+  for (uint32_t g = static_cast<uint32_t>(g_first) + threadIdx.x; g < g_stop; g += CF_BLOCK) {
     float z[6];
     uint32_t unused = 0;
-    normals6_f32_impl<true, 3>(static_cast<uint32_t>(g), F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+    normals6_f32_impl<true, 3>(g, F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+    if (g >= g_in0 && g < g_in1) {
 #pragma unroll
-    for (int u = 0; u < G; ++u) {
-      float state = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
+      for (int u = 0; u < G; ++u) acc[u] += static_cast<double>(put_of(z, u));
+    } else {
 #pragma unroll
-      for (int i = 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
-      const float val = SCHEME == SMC_LOG_EULER ? k.X0 * mufu_ex2(fmaf(k.lin1, state, k.lin0)) : state;
-      const float diff = k.K - val;
-      const float put = k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
-      const int64_t path = g * G + u;
-      acc[u] += (path >= p0 && path < p1) ? static_cast<double>(put) : 0.0;
+      for (int u = 0; u < G; ++u) {
+        const int64_t path = static_cast<int64_t>(g) * G + u;
+        if (path >= p0 && path < p1) acc[u] += static_cast<double>(put_of(z, u));
+      }
     }
   }
 #pragma unroll
