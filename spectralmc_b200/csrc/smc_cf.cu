@@ -1,5 +1,5 @@
 // Fused batch path and CF estimate: in-register Philox normals -> GBM stepping -> payoff ->
-// column sums over batches -> one FFT per contract, as ONE persistent kernel per step.
+// column sums over batches -> one FFT per contract, as ONE kernel per step.
 //
 // Replaces, per training step, the reference's Python loop
 //   [ _simulate_fft(c) for c in sobol_inputs ] + cp.asarray(fft_values)
@@ -8,11 +8,12 @@
 // and, for materialised inputs, cp.mean(cp.fft.fft(mat, axis=1), axis=0) (gbm_trainer.py:814-817).
 //
 // Structure (all reductions fixed-order, no float atomics => bit-reproducible):
-//   step_kernel      a persistent grid of co-resident CTAs (occupancy x SM count) draws work items
-//                    (contract, tile of batch rows) from a device counter.  Thread (r, col) owns
-//                    column `col` of the [B, N] payoff matrix and walks rows r, r+R, ... of its tile,
-//                    accumulating in float64; the CTA folds the R row-lanes in shared memory and
-//                    writes one partial column-sum vector per tile.
+//   step_kernel      one CTA per (contract, tile of batch rows), handed out by the hardware block
+//                    scheduler.  The first CTAs to reach a contract form its constants and publish
+//                    them in a table; nobody waits for them.  Thread (r, col) owns column `col` of the
+//                    [B, N] payoff matrix and walks rows r, r+R, ... of its tile, accumulating in
+//                    float64; the CTA folds the R row-lanes in shared memory and writes one partial
+//                    column-sum vector per tile.  (Short paths, timesteps <= 3: grouped_short_tile.)
 //   ticket tree      the tile vectors of a contract are the leaves of a radix-16 tree.  A CTA that
 //                    completes a vector takes a ticket (atomic counter) on its parent; whoever takes
 //                    the LAST ticket of a node folds that node's children in index order (so the sum
@@ -21,18 +22,16 @@
 //                    (mean_b FFT_n(mat) == FFT_n(mean_b mat)) in float64 shared memory (radix-2 for
 //                    powers of two, table-driven DFT otherwise) and narrows to the output width —
 //                    or, for batch-sharded multi-GPU runs, pushes the real vector into every peer's
-//                    exchange buffer; a second phase of the same kernel sums the peers' vectors.
+//                    exchange buffer; a small collect kernel then sums the peers' vectors in rank order.
 //   Large N (transform working set > 16 KiB of shared memory) keeps the transform in a separate
 //   one-CTA-per-contract kernel (cf_finalize_kernel / cf_exchange_finalize_kernel).
 // Tile and tree shapes are functions of the problem shape only (never of the SM count), and a
 // tile's vector does not depend on which CTA computed it, so results do not depend on the device
-// the job lands on or on the dynamic schedule.
+// the job lands on or on the order in which CTAs run.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
-#include <vector>
 
 #include "smc_device.cuh"
 #include "smc_internal.h"
@@ -956,10 +955,10 @@ __global__ void __launch_bounds__(CF_BLOCK)
 //            `world` vectors in rank order — every rank forms the identical float64 sum — and takes the
 //            ONE transform.
 // The exchange therefore moves n doubles per contract and rank (half of what the complex all-reduce
-// moves), carries the sum in float64, and costs no launch and no host involvement.
-// Deadlock freedom: the grid is persistent and never larger than the number of co-resident CTAs;
-// every CTA leaves the tile loop — where all pushes happen and nothing waits — before it waits in
-// phase 2, so every flag a peer waits for is written by a CTA that is already running.  Slots
+// moves), carries the sum in float64, and costs one small launch and no host involvement.
+// Deadlock freedom: phase 1 runs inside the step kernel and never waits; phase 2 is a kernel of its
+// own, launched behind it on the same stream and never larger than the number of co-resident CTAs, so
+// every flag a peer waits for is written by a kernel that is already running or complete.  Slots
 // alternate with the epoch parity: a rank can be at most one call ahead of a peer, because its phase 2
 // of call k needs that peer's phase 1 of call k.  A wait is bounded in TIME (PeerExchange::timeout_ns,
 // default two minutes): a peer that never arrives yields NaN targets and a status word, not a trap.

@@ -108,3 +108,36 @@ def test_peer_exchange_argument_validation_needs_no_device() -> None:
     args.normalization = _cabi.SMC_NORMALIZE
     assert call() == 1 and b"NORMALIZE" in _cabi.LIB.smc_last_error()
     assert check(1 << 20) == 1 and b"NORMALIZE" in _cabi.LIB.smc_last_error()
+
+
+def test_tile_plan_depends_on_the_problem_shape_only() -> None:
+    """How a simulation is cut into CTAs (smc_cf_fused_plan, no device): tiles cover the local rows exactly, are
+    multiples of the row-lane count, never smaller than 16 384 path-steps, and the ticket tree ends in a root of at
+    most 16 vectors — at BASELINE's shapes and at ragged ones."""
+    from spectralmc_b200 import _cabi
+
+    torch = __import__("torch")
+    shapes = {"c1": (1, 12, 16, 64, torch.float64), "c2": (1, 252, 128, 65536, torch.float32), "c3": (1024, 1, 16, 4096, torch.float32),
+              "c4": (512, 365, 256, 4096, torch.float64), "c5 share": (4096, 252, 128, 131072, torch.float32),
+              "ragged": (3, 7, 24, 1001, torch.float32), "wide": (2, 5, 1000, 77, torch.float64)}
+    for name, (C, T, N, B, dtype) in shapes.items():
+        for lo, hi in ((0, B), (B // 3, B - B // 5)):
+            args = _cabi.make_fused_args(None, C, T, N, B, dtype, 0, _cabi.SMC_RAW, 7, 0, batch_begin=lo, batch_end=hi)
+            args.contracts = 16
+            plan = _cabi.cf_fused_plan(args)
+            rows = hi - lo
+            assert plan["row_lanes"] == max(1, 256 // min(N, 256)), name
+            assert plan["tile_rows"] % plan["row_lanes"] == 0 and plan["tile_rows"] >= 1, name
+            assert (plan["tiles"] - 1) * plan["tile_rows"] < rows <= plan["tiles"] * plan["tile_rows"], (name, plan, rows)
+            assert plan["tile_rows"] * N * T >= 16384 or plan["tiles"] == 1, (name, plan)
+            assert 1 <= plan["root_fan_in"] <= 16, (name, plan)
+            width, level = plan["tiles"], 0
+            while width > 16:
+                width, level = -(-width // 16), level + 1
+            assert (level, width) == (plan["levels"], plan["root_fan_in"]), (name, plan)
+            assert _cabi.LIB.smc_cf_fused_workspace_bytes(ctypes.byref(args)) >= plan["tiles"] * C * N * 8
+    c2 = _cabi.make_fused_args(None, 1, 252, 128, 65536, torch.float32, 0, _cabi.SMC_RAW, 7, 0)
+    c2.contracts = 16
+    assert _cabi.LIB.smc_cf_fused_launch_count(ctypes.byref(c2)) == 1  # the RAW step is ONE kernel
+    c2.normalization = _cabi.SMC_NORMALIZE
+    assert _cabi.LIB.smc_cf_fused_launch_count(ctypes.byref(c2)) == 2
