@@ -223,11 +223,16 @@ __device__ __forceinline__ SimConsts<Real> make_consts(const TileParams& p, cons
 }
 
 // Per-contract constants (float64 exp/sqrt/divide, out of line so the hot kernel's register allocation
-// does not see them) are formed by whichever CTAs reach a contract first and shared with every later
-// CTA through a table in the workspace: `ready[c]` (zeroed before the launch) is set with release
-// semantics once table[c] is written.  A thread that finds the flag clear does not wait — it computes
-// the same values itself — so nothing depends on the order in which CTAs are scheduled, and neither route
-// contains a barrier (threads of one CTA may see different flag values).
+// does not see them) are formed by ONE thread of whichever CTAs reach a contract first and shared with
+// every later CTA through a table in the workspace: `ready[c]` (zeroed before the launch) is set with
+// release semantics once table[c] is written.  A CTA that finds the flag clear does not wait for another
+// CTA — its own thread 0 computes the same values and hands them to the CTA through shared memory — so
+// nothing depends on the order in which CTAs are scheduled.  The CTA decides once (barrier + vote): threads
+// of one CTA may read different flag values, and a thread that read "clear" is ordered behind the publisher
+// through the barrier with a thread that acquired "set".
+// (Every thread computing the constants itself was measured first: with four tiles per contract, as at the
+// reference's test size, all four CTAs start before the first publishes, and 8 warps x ~500 instructions of
+// float64 code per CTA were half of the short-path kernel's time.)
 template <typename Real>
 static __device__ __noinline__ void compute_consts(const TileParams& p, int64_t c_local, SimConsts<Real>* out) {
   *out = make_consts<Real>(p, p.scheme, p.contract0 + c_local, c_local);
@@ -242,20 +247,24 @@ __device__ __forceinline__ void store_release_gpu(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// `slot`: shared memory for one SimConsts<Real>, free again on return
 template <typename Real>
-__device__ __forceinline__ SimConsts<Real> contract_consts(const TileParams& p, int64_t c_local) {
+__device__ __forceinline__ SimConsts<Real> contract_consts(const TileParams& p, int64_t c_local, SimConsts<Real>* slot) {
   Real* table = reinterpret_cast<Real*>(static_cast<SimConsts<Real>*>(p.consts) + c_local);
   SimConsts<Real> k;
-  if (load_acquire_gpu(p.consts_ready + c_local) != 0u) {
+  if (__syncthreads_or(load_acquire_gpu(p.consts_ready + c_local) != 0u)) {
     k.X0 = __ldcg(table + 0); k.K = __ldcg(table + 1); k.df = __ldcg(table + 2); k.scale = __ldcg(table + 3);
     k.lin0 = __ldcg(table + 4); k.lin1 = __ldcg(table + 5);
-  } else {
-    compute_consts<Real>(p, c_local, &k);
-    if (threadIdx.x == 0) {
-      table[0] = k.X0; table[1] = k.K; table[2] = k.df; table[3] = k.scale; table[4] = k.lin0; table[5] = k.lin1;
-      store_release_gpu(p.consts_ready + c_local, 1u);
-    }
+    return k;
   }
+  if (threadIdx.x == 0) {
+    compute_consts<Real>(p, c_local, slot);
+    table[0] = slot->X0; table[1] = slot->K; table[2] = slot->df; table[3] = slot->scale; table[4] = slot->lin0; table[5] = slot->lin1;
+    store_release_gpu(p.consts_ready + c_local, 1u);
+  }
+  __syncthreads();
+  k = *slot;
+  __syncthreads();  // the slot is scratch the caller reuses
   return k;
 }
 
@@ -723,9 +732,16 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
   // groups [g_in0, g_in1) lie wholly inside the tile and need no per-path range check; at most the first and the
   // last group of a tile are cut by its boundary (a cut group is drawn by both tiles, each keeping its own lanes)
   const uint32_t g_in0 = static_cast<uint32_t>((p0 + G - 1) / G), g_in1 = static_cast<uint32_t>(p1 / G);
+  // Payoffs are summed in float32 for at most SHORT_FLUSH consecutive groups per lane and then folded into the
+  // float64 accumulator: the float32 -> float64 conversion is an XU-pipe instruction, and at one timestep this
+  // kernel is XU-bound (12 MUFU of Box-Muller + 6 MUFU.EX2 per block; six conversions per block were a quarter of
+  // the pipe's work).  Eight non-negative terms add a relative error of at most 7 * 2^-24 to a run — the size of
+  // the float32 payoff's own rounding — and the order is fixed, so bit-reproducibility is untouched.
+  constexpr int SHORT_FLUSH = 8;
   double acc[G];
+  float run[G];
 #pragma unroll
-  for (int u = 0; u < G; ++u) acc[u] = 0.0;
+  for (int u = 0; u < G; ++u) acc[u] = 0.0, run[u] = 0.0f;
   auto put_of = [&](const float (&z)[6], int u) {
     float state = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
 #pragma unroll
@@ -735,50 +751,68 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
     return k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
   };
   const uint32_t g_stop = static_cast<uint32_t>(g_end);  // g_end <= 2^32 / G + 1
-  for (uint32_t g = static_cast<uint32_t>(g_first) + threadIdx.x; g < g_stop; g += CF_BLOCK) {
-    float z[6];
-    uint32_t unused = 0;
-    normals6_f32_impl<true, 3>(g, F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+  auto add_group = [&](uint32_t g, const float (&z)[6]) {
     if (g >= g_in0 && g < g_in1) {
 #pragma unroll
-      for (int u = 0; u < G; ++u) acc[u] += static_cast<double>(put_of(z, u));
+      for (int u = 0; u < G; ++u) run[u] += put_of(z, u);
     } else {
 #pragma unroll
       for (int u = 0; u < G; ++u) {
         const int64_t path = static_cast<int64_t>(g) * G + u;
-        if (path >= p0 && path < p1) acc[u] += static_cast<double>(put_of(z, u));
+        if (path >= p0 && path < p1) run[u] += put_of(z, u);
       }
     }
+  };
+  auto flush = [&]() {
+#pragma unroll
+    for (int u = 0; u < G; ++u) acc[u] += static_cast<double>(run[u]), run[u] = 0.0f;
+  };
+  // (drawing two groups per iteration with packed Box-Muller pairs, as the long-path loop does, was measured: no gain —
+  // this loop is bound by its instruction count, profiles/r2_short_path_notes.md)
+  int pending = 0;
+  uint32_t g = static_cast<uint32_t>(g_first) + threadIdx.x;
+  for (; g < g_stop; g += CF_BLOCK) {
+    float z[6];
+    uint32_t unused = 0;
+    normals6_f32_impl<true, 3>(g, F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+    add_group(g, z);
+    if (++pending >= SHORT_FLUSH) {
+      pending = 0;
+      flush();
+    }
   }
+#pragma unroll
+  for (int u = 0; u < G; ++u) acc[u] += static_cast<double>(run[u]);
 #pragma unroll
   for (int u = 0; u < G; ++u) lanes[threadIdx.x * G + u] = acc[u];
   __syncthreads();
   // entry e = t G + u belongs to column (o + e) mod N, o = (g_first G) mod N; column `col` owns entries
   // e0, e0 + N, ... (count per column = 256 G / N).  `subs` threads share a column, then fold in order.
-  const int64_t n = p.n;
-  const int64_t o = (g_first * G) % n;
-  const int64_t per_col = static_cast<int64_t>(CF_BLOCK) * G / n;
+  // (32-bit index arithmetic: this runs once per CTA, and at the reference's test size a CTA is short)
+  const uint32_t n = static_cast<uint32_t>(p.n);
+  const uint32_t o = (static_cast<uint32_t>(g_first % n) * G) % n;
+  const uint32_t per_col = static_cast<uint32_t>(CF_BLOCK) * G / n;
   if (n <= CF_BLOCK) {
-    const int subs = CF_BLOCK / static_cast<int>(n);
-    const int sub = threadIdx.x / static_cast<int>(n), col = threadIdx.x - sub * static_cast<int>(n);
+    const uint32_t subs = CF_BLOCK / n;
+    const uint32_t sub = threadIdx.x / n, col = threadIdx.x - sub * n;
     double s = 0.0;
     if (sub < subs) {
-      const int64_t e0 = (col - o + n) % n;
-      for (int64_t m = sub; m < per_col; m += subs) s += lanes[e0 + m * n];
+      const uint32_t e0 = col >= o ? col - o : col + n - o;
+      for (uint32_t m = sub; m < per_col; m += subs) s += lanes[e0 + m * n];
     }
     sm[threadIdx.x] = s;
     __syncthreads();
     if (sub == 0) {
       double tot = 0.0;
-      for (int q = 0; q < subs; ++q) tot += sm[q * n + col];
+      for (uint32_t q = 0; q < subs; ++q) tot += sm[q * n + col];
       dst[col] = tot;
     }
     __syncthreads();
   } else {
-    for (int64_t col = threadIdx.x; col < n; col += CF_BLOCK) {
-      const int64_t e0 = (col - o + n) % n;
+    for (uint32_t col = threadIdx.x; col < n; col += CF_BLOCK) {
+      const uint32_t e0 = col >= o ? col - o : col + n - o;
       double s = 0.0;
-      for (int64_t m = 0; m < per_col; ++m) s += lanes[e0 + m * n];
+      for (uint32_t m = 0; m < per_col; ++m) s += lanes[e0 + m * n];
       dst[col] = s;
     }
     __syncthreads();
@@ -791,6 +825,9 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
 #ifndef SMC_F32_FUSED_MIN_CTAS_OTHER
 #define SMC_F32_FUSED_MIN_CTAS_OTHER 5  // simple-Euler / stepwise / terminal-staging instantiations: 5 measured best
 #endif
+#ifndef SMC_F32_SHORT_MIN_CTAS
+#define SMC_F32_SHORT_MIN_CTAS 6  // short-path grouped tile: 6 CTAs x 40 registers measured best of {3,4,5,6} (profiles/r2_short_path_notes.md)
+#endif
 #ifndef SMC_F32_FUSED_MIN_CTAS_TERMINAL
 #define SMC_F32_FUSED_MIN_CTAS_TERMINAL 4  // log-Euler with staged terminals (NORMALIZE pass A): 1.360 ms at c2 vs 1.445 at 5
 #endif
@@ -802,7 +839,7 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
 // FORM (float32 fused kernels): 0 = timesteps a multiple of 6, no tail code in the kernel; 1 = general;
 // 2 = short paths (timesteps <= 3) in the grouped layout, one Philox block per G = 6 / timesteps paths.
 template <typename Real, int SRC, int SCHEME, int OUT, int FORM = 1>
-__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (FORM == 2 ? SMC_F32_FUSED_MIN_CTAS_OTHER : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER))))
+__global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real) == 8 ? SMC_F64_FUSED_MIN_CTAS : (FORM == 2 ? SMC_F32_SHORT_MIN_CTAS : (SCHEME == SMC_LOG_EULER ? (OUT == OUT_COLSUM ? SMC_F32_FUSED_MIN_CTAS : SMC_F32_FUSED_MIN_CTAS_TERMINAL) : SMC_F32_FUSED_MIN_CTAS_OTHER))))
     step_kernel(const __grid_constant__ TileParams p) {
   extern __shared__ double dyn[];
   __shared__ double sm[CF_BLOCK];
@@ -815,7 +852,7 @@ __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real)
   constexpr bool RAGGED = FORM != 0;
 
   SimConsts<Real> k{};
-  if (SRC != SRC_MATRIX) k = contract_consts<Real>(p, c_local);
+  if (SRC != SRC_MATRIX) k = contract_consts<Real>(p, c_local, reinterpret_cast<SimConsts<Real>*>(sm));
   const uint64_t mi = p.first_matrix_index + static_cast<uint64_t>(c_global);
   const uint32_t k_lo = static_cast<uint32_t>(mi), k_hi = static_cast<uint32_t>(mi >> 32);
 
