@@ -39,10 +39,13 @@ inline PhiloxKeys make_philox_keys(uint64_t seed) {
 // (path column, row group q, matrix_index lo, matrix_index hi | dtype bit).  c1 is the only
 // word that changes inside a path's time loop; it sits in an XOR slot so that both first-round
 // products and one second-round product are loop-invariant (17 IMAD.WIDE per block, not 20).
+#ifndef SMC_PHILOX_ROUNDS
+#define SMC_PHILOX_ROUNDS 10  // EVALUATION builds only (profiles/r2_philox7_evaluation.md): the shipped stream is Philox4x32-10
+#endif
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& key, uint32_t (&out)[4]) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < SMC_PHILOX_ROUNDS; ++r) {
     const uint64_t p0 = static_cast<uint64_t>(PHILOX_M0) * c0;  // IMAD.WIDE.U32
     const uint64_t p1 = static_cast<uint64_t>(PHILOX_M1) * c2;
     const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ key.k0[r];  // LOP3
