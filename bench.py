@@ -496,10 +496,10 @@ def secondary_workloads(_cabi, torch, dev, calib: dict, args) -> dict:
     """The other BASELINE.json configurations and variants on this GPU (N = 1 only), each with its own roofline."""
     import numpy as np
 
-    def time_fused(c, t, n, b, dtype, scheme, norm, steps, contracts_rows=None):
+    def time_fused(c, t, n, b, dtype, scheme, norm, steps, contracts_rows=None, stream_version=0):
         rows = np.tile(np.asarray(CANON, dtype=np.float64), (c, 1)) if contracts_rows is None else contracts_rows
         contracts = torch.tensor(rows, device=dev)
-        a = _cabi.make_fused_args(contracts, c, t, n, b, dtype, scheme, norm, 7, 0)
+        a = _cabi.make_fused_args(contracts, c, t, n, b, dtype, scheme, norm, 7, 0, stream_version=stream_version)
         work = torch.empty(int(_cabi.LIB.smc_cf_fused_workspace_bytes(_cabi.byref(a))) + 4096, dtype=torch.uint8, device=dev)
         _cabi.cf_fused(a, dev, dtype, work)
         torch.cuda.synchronize()
@@ -523,6 +523,11 @@ def secondary_workloads(_cabi, torch, dev, calib: dict, args) -> dict:
     ms, k = time_fused(1, c2["T"], c2["N"], c2["B"], torch.float32, _cabi.SMC_SIMPLE_EULER, _cabi.SMC_RAW, 10)
     out["c2_simple_euler"] = {"ms": ms, "path_steps_per_sec": steps2 / (ms * 1e-3), "kernels": k,
                               "roofline": {"bound": "xu", "frac": steps2 / (ms * 1e-3) * XU_OPS_PER_STEP / calib["mufu"], "unit": "of calibrated MUFU peak, whole step"}}
+    # the opt-in Philox4x32-7 stream (smc_stream_version 1): NOT the stream `value` is measured on — a different sample set
+    ms, k = time_fused(1, c2["T"], c2["N"], c2["B"], torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 10, stream_version=_cabi.SMC_STREAM_PHILOX7)
+    out["c2_philox7_opt_in"] = {"ms": ms, "path_steps_per_sec": steps2 / (ms * 1e-3), "kernels": k,
+                                "note": "opt-in stream_version=1 (seven Philox rounds; passes the same battery, tests/test_gpu_stream_battery.py); every other number in this line is the default Philox4x32-10 stream",
+                                "roofline": {"bound": "xu", "frac": steps2 / (ms * 1e-3) * XU_OPS_PER_STEP / calib["mufu"], "unit": "of calibrated MUFU peak, whole step"}}
     # c4: 512 Sobol contracts, float64 (BASELINE configs[3]); FP64-pipe roofline from the live DFMA calibration
     c4 = WORKLOADS["c4"]
     from spectralmc_b200.gbm import BlackScholes

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define SMC_VERSION 101 /* 0.1.1 */
+#define SMC_VERSION 102 /* 0.1.2 */
 
 enum smc_status {
   SMC_OK = 0,
@@ -54,6 +54,13 @@ enum smc_scheme {
   SMC_LOG_EULER_STEPWISE = 2
 };
 enum smc_normalization { SMC_NORMALIZE = 0, SMC_RAW = 1 };
+/* Which counter-based generator draws the normals (the stream is this library's own specification,
+ * oracle/philox.py; element (i, j) of matrix k is a pure function of (seed, k, i, j, stream_version)).
+ * PHILOX10 is the default everywhere and the stream every published number is measured on.  PHILOX7 is an
+ * OPT-IN: the same construction with seven Philox rounds (the fewest that pass BigCrush, Salmon et al. SC'11;
+ * it passes this repository's own battery, profiles/r2_philox7_evaluation.md) and about 13 % faster in the
+ * fused float32 kernel.  It is a DIFFERENT sample set: never selected implicitly. */
+enum smc_stream_version { SMC_STREAM_PHILOX10 = 0, SMC_STREAM_PHILOX7 = 1 };
 /* how the CF estimate is formed from the [B, N] payoff matrix */
 enum smc_cf_method {
   SMC_CF_MEAN_THEN_FFT = 0, /* FFT_n(mean_b mat): one length-N transform (linearity)          */
@@ -76,6 +83,9 @@ int smc_device_info(int* sm_count, int* cc_major, int* cc_minor);
  */
 int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
                        uint64_t matrix_index, void* stream);
+/* the same with an explicit generator (smc_stream_version); smc_philox_normals is stream_version 0 */
+int smc_philox_normals_v(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
+                         uint64_t matrix_index, int stream_version, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K2  path kernel — replaces the Numba launch
@@ -173,6 +183,7 @@ typedef struct smc_fused_args {
   int normalization;
   uint64_t seed;             /* SimulationParams.mc_seed (gbm.py:84)                         */
   uint64_t first_matrix_index; /* SimulationParams.skip (gbm.py:86) at the first contract     */
+  int stream_version;        /* smc_stream_version; 0 (zero-initialised) = Philox4x32-10      */
 } smc_fused_args;
 
 size_t smc_cf_fused_workspace_bytes(const smc_fused_args* args);
@@ -337,9 +348,9 @@ int smc_cvnn_train_step(const smc_cvnn_net* net, void* params, void* grads, void
  * horizontally adjacent entries z[i,j] z[i,j+1] (pairs inside one warp of 32 columns). */
 int smc_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols,
                                uint32_t* radius_hist, uint32_t* angle_hist, uint64_t* tails4, double* power_sums4,
-                               void* stream);
+                               int stream_version, void* stream);
 int smc_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7,
-                             void* stream);
+                             int stream_version, void* stream);
 
 /* Pipe-peak calibration microbenchmarks (FP32 FMA issue and MUFU/XU), used by bench.py to
  * state the compute roofline on the box it runs on: each runs `iters` dependent-chain

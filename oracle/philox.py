@@ -37,6 +37,10 @@ Stream definition
 * Box–Muller: r = sqrt(-2 ln u1), theta = 2 pi (u2 - 0.5); even row = r cos(theta),
   odd row = r sin(theta).
 
+* ``stream_version`` (include/spectralmc_b200.h): 0 = everything above on Philox4x32-10, the default and the stream every
+  published number is measured on; 1 = the identical construction on Philox4x32-7 (the fewest rounds that pass BigCrush
+  in Salmon et al.; an explicit opt-in, a different sample set, profiles/r2_philox7_evaluation.md).
+
 Philox4x32-10 follows Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"
 (SC'11) — multipliers 0xD2511F53 / 0xCD9E8D57, Weyl key increments 0x9E3779B9 /
 0xBB67AE85 — and is checked against the Random123 known-answer vectors in
@@ -55,8 +59,11 @@ _MASK32 = np.uint64(0xFFFFFFFF)
 F64_STREAM_BIT = 0x80000000
 
 
-def philox4x32_10(ctr, key):
-    """Philox4x32-10 on arrays of counters.
+STREAM_ROUNDS = {0: 10, 1: 7}  # smc_stream_version -> Philox rounds (include/spectralmc_b200.h)
+
+
+def philox4x32_10(ctr, key, rounds: int = 10):
+    """Philox4x32-``rounds`` (10 unless stated) on arrays of counters.
 
     ``ctr``: 4 broadcastable uint32 arrays (c0, c1, c2, c3); ``key``: 2 ints.
     Returns 4 uint32 arrays.
@@ -64,7 +71,7 @@ def philox4x32_10(ctr, key):
     c0, c1, c2, c3 = np.broadcast_arrays(*[np.asarray(c, dtype=np.uint32) for c in ctr])
     c0, c1, c2, c3 = (c.astype(np.uint64) for c in (c0, c1, c2, c3))
     k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = M0 * c0  # 64-bit product, fits (both < 2**32)
         p1 = M1 * c2
         hi0, lo0 = p0 >> np.uint64(32), p0 & _MASK32
@@ -136,6 +143,7 @@ def normals_matrix(
     col_begin: int = 0,
     col_end: int | None = None,
     return_radius: bool = False,
+    stream_version: int = 0,
 ):
     """The ``matrix_index``-th ``(rows, cols)`` standard-normal matrix of stream ``seed``.
 
@@ -143,8 +151,10 @@ def normals_matrix(
     global column index, so a slice equals the same slice of the full matrix).
     With ``return_radius`` also returns the Box–Muller radius per element (used by the
     tests to form error bounds for the MUFU-based float32 device path).
+    ``stream_version`` 1 is the opt-in stream: the identical construction on Philox4x32-7.
     """
     dtype = np.dtype(dtype)
+    rounds = STREAM_ROUNDS[stream_version]
     col_end = cols if col_end is None else col_end
     j = np.arange(col_begin, col_end, dtype=np.uint64).astype(np.uint32)[None, :]
     k_lo, k_hi = matrix_index & 0xFFFFFFFF, (matrix_index >> 32) & 0x7FFFFFFF
@@ -159,13 +169,13 @@ def normals_matrix(
         else:
             nq = (rows + 5) // 6
             q = np.arange(nq, dtype=np.uint32)[:, None]
-        x = philox4x32_10((j, q, k_lo, k_hi), key)
+        x = philox4x32_10((j, q, k_lo, k_hi), key, rounds)
         radius, angle = f32_fields(*x)
         u1 = [uniform_21(r) for r in radius]
         need = (radius[0] == 0) | (radius[1] == 0) | (radius[2] == 0)
         if need.any():  # the rare refinement block
             qq, jj = np.nonzero(need)
-            y = philox4x32_10((j[0, jj], q[qq, 0] | np.uint32(F32_REFINE_BIT), k_lo, k_hi), key)
+            y = philox4x32_10((j[0, jj], q[qq, 0] | np.uint32(F32_REFINE_BIT), k_lo, k_hi), key, rounds)
             for p in range(3):
                 hit = radius[p][qq, jj] == 0
                 u1[p][qq[hit], jj[hit]] = uniform_refined(y[p][hit])
@@ -187,7 +197,7 @@ def normals_matrix(
     elif dtype == np.float64:
         nq = (rows + 1) // 2
         q = np.arange(nq, dtype=np.uint32)[:, None]
-        x0, x1, x2, x3 = philox4x32_10((j, q, k_lo, F64_STREAM_BIT | k_hi), key)
+        x0, x1, x2, x3 = philox4x32_10((j, q, k_lo, F64_STREAM_BIT | k_hi), key, rounds)
         za, zb, ra = _box_muller(uniform_f64(x0, x1), uniform_f64(x2, x3))
         z = np.stack([za, zb], axis=1).reshape(2 * nq, -1)[:rows]
         rad = np.stack([ra, ra], axis=1).reshape(2 * nq, -1)[:rows]

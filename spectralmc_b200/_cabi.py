@@ -24,9 +24,10 @@ SMC_LOG_EULER, SMC_SIMPLE_EULER, SMC_LOG_EULER_STEPWISE = 0, 1, 2
 SMC_NORMALIZE, SMC_RAW = 0, 1
 SMC_CF_MEAN_THEN_FFT, SMC_CF_ROW_FFT = 0, 1
 SMC_EINVAL = 1
+SMC_STREAM_PHILOX10, SMC_STREAM_PHILOX7 = 0, 1
 
 EXPORTS = (
-    "smc_version smc_last_error smc_device_info smc_philox_normals smc_gbm_paths_inplace "
+    "smc_version smc_last_error smc_device_info smc_philox_normals smc_philox_normals_v smc_gbm_paths_inplace "
     "smc_gbm_terminal_from_normals smc_normalize_rows_workspace_bytes smc_normalize_rows smc_payoff "
     "smc_means3_workspace_bytes smc_means3 smc_cf_fft_mean_workspace_bytes smc_cf_fft_mean smc_fft_rows "
     "smc_cf_fused_workspace_bytes smc_cf_fused_launch_count smc_cf_fused smc_fused_terminal_workspace_bytes smc_fused_terminal "
@@ -66,6 +67,7 @@ class FusedArgs(Structure):
         ("normalization", c_int),
         ("seed", c_uint64),
         ("first_matrix_index", c_uint64),
+        ("stream_version", c_int),
     ]
 
 
@@ -162,8 +164,9 @@ def _load() -> ctypes.CDLL:
     lib.smc_p2p_free.argtypes = [c_void_p]
     lib.smc_cf_fused_p2p.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_void_p, c_void_p, c_size_t, c_void_p]
     lib.smc_p2p_allreduce_sum_f64.argtypes = [c_void_p, c_int64, POINTER(P2PGroup), c_void_p]
-    lib.smc_diag_stream_fields_f32.argtypes = [c_uint64, c_uint64, c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
-    lib.smc_diag_stream_lags_f32.argtypes = [c_uint64, c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_void_p]
+    lib.smc_diag_stream_fields_f32.argtypes = [c_uint64, c_uint64, c_uint64, ctypes.c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]
+    lib.smc_diag_stream_lags_f32.argtypes = [c_uint64, c_uint64, ctypes.c_uint32, ctypes.c_uint32, c_void_p, c_int, c_void_p]
+    lib.smc_philox_normals_v.argtypes = [c_void_p, c_int64, c_int64, c_int, c_uint64, c_uint64, c_int, c_void_p]
     lib.smc_cf_fused_plan.argtypes = [POINTER(FusedArgs), POINTER(c_int64), c_int]
     lib.smc_cf_fused_p2p_check.argtypes = [POINTER(FusedArgs), POINTER(P2PGroup), c_size_t]
     lib.smc_p2p_status.argtypes = [POINTER(P2PGroup), POINTER(ctypes.c_uint32), c_void_p]
@@ -283,11 +286,12 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- wrappers
-def philox_normals(out: torch.Tensor, seed: int, matrix_index: int) -> torch.Tensor:
-    """K1: fill ``out`` (rows, cols) with the ``matrix_index``-th matrix of stream ``seed``."""
+def philox_normals(out: torch.Tensor, seed: int, matrix_index: int, stream_version: int = SMC_STREAM_PHILOX10) -> torch.Tensor:
+    """K1: fill ``out`` (rows, cols) with the ``matrix_index``-th matrix of stream ``seed`` (``stream_version``:
+    Philox4x32-10 by default, Philox4x32-7 as an explicit opt-in)."""
     _require_cuda(out, "out")
     rows, cols = out.shape
-    check(LIB.smc_philox_normals(out.data_ptr(), rows, cols, dtype_code(out.dtype), seed, matrix_index, _stream()))
+    check(LIB.smc_philox_normals_v(out.data_ptr(), rows, cols, dtype_code(out.dtype), seed, matrix_index, stream_version, _stream()))
     return out
 
 
@@ -398,6 +402,7 @@ def make_fused_args(
     first_matrix_index: int,
     batch_begin: int = 0,
     batch_end: int | None = None,
+    stream_version: int = SMC_STREAM_PHILOX10,
 ) -> FusedArgs:
     return FusedArgs(
         contracts.data_ptr() if contracts is not None else None,
@@ -412,6 +417,7 @@ def make_fused_args(
         normalization,
         seed,
         first_matrix_index,
+        stream_version,
     )
 
 
@@ -573,20 +579,22 @@ def cvnn_train_step(net: CvnnNet, params: torch.Tensor, grads: torch.Tensor, exp
 
 
 # --------------------------------------------------------------------------- stream audit
-def diag_stream_fields(seed: int, matrix_index: int, n_blocks: int, cols: int, device: torch.device) -> dict:
+def diag_stream_fields(seed: int, matrix_index: int, n_blocks: int, cols: int, device: torch.device,
+                       stream_version: int = SMC_STREAM_PHILOX10) -> dict:
     """Field histograms, tail counts and power sums of ``6 * n_blocks`` float32-stream normals (no matrix in HBM)."""
     radius = torch.zeros(1 << 21, dtype=torch.int32, device=device)
     angle = torch.zeros(1 << 21, dtype=torch.int32, device=device)
     tails = torch.zeros(4, dtype=torch.int64, device=device)
     sums = torch.zeros(4, dtype=torch.float64, device=device)
     check(LIB.smc_diag_stream_fields_f32(seed, matrix_index, n_blocks, cols, radius.data_ptr(), angle.data_ptr(), tails.data_ptr(),
-                                         sums.data_ptr(), _stream()))
+                                         sums.data_ptr(), stream_version, _stream()))
     return {"radius_hist": radius, "angle_hist": angle, "tails": tails, "power_sums": sums}
 
 
-def diag_stream_lags(seed: int, matrix_index: int, cols: int, rows: int, device: torch.device) -> torch.Tensor:
+def diag_stream_lags(seed: int, matrix_index: int, cols: int, rows: int, device: torch.device,
+                     stream_version: int = SMC_STREAM_PHILOX10) -> torch.Tensor:
     sums = torch.zeros(7, dtype=torch.float64, device=device)
-    check(LIB.smc_diag_stream_lags_f32(seed, matrix_index, cols, rows, sums.data_ptr(), _stream()))
+    check(LIB.smc_diag_stream_lags_f32(seed, matrix_index, cols, rows, sums.data_ptr(), stream_version, _stream()))
     return sums
 
 

@@ -61,10 +61,11 @@ class ConcurrentNormGeneratorConfig:
     seed: int
     dtype: Precision
     skips: int = 0
+    stream_version: int = 0  # 0: Philox4x32-10 (default); 1: the opt-in Philox4x32-7 stream (include/spectralmc_b200.h)
 
     @classmethod
     def create(
-        cls, *, rows: int, cols: int, seed: int, dtype: Precision, skips: int = 0
+        cls, *, rows: int, cols: int, seed: int, dtype: Precision, skips: int = 0, stream_version: int = 0
     ) -> Result["ConcurrentNormGeneratorConfig", InvalidShape | SeedOutOfRange]:
         if rows <= 0 or cols <= 0:
             return Failure(InvalidShape(rows=rows, cols=cols))
@@ -72,14 +73,16 @@ class ConcurrentNormGeneratorConfig:
             return Failure(SeedOutOfRange(seed=seed))
         if skips < 0:
             return Failure(SeedOutOfRange(seed=skips))
-        return Success(cls(rows=rows, cols=cols, seed=seed, dtype=dtype, skips=skips))
+        if stream_version not in (0, 1):
+            raise ValueError(f"stream_version must be 0 (Philox4x32-10) or 1 (Philox4x32-7); got {stream_version}")
+        return Success(cls(rows=rows, cols=cols, seed=seed, dtype=dtype, skips=skips, stream_version=stream_version))
 
 
 class _NormGenerator:
     """One worker: fills matrices on its own CUDA stream (reference :173-256)."""
 
-    def __init__(self, rows: int, cols: int, *, dtype: torch.dtype) -> None:
-        self._rows, self._cols, self._dtype = rows, cols, dtype
+    def __init__(self, rows: int, cols: int, *, dtype: torch.dtype, stream_version: int = 0) -> None:
+        self._rows, self._cols, self._dtype, self._stream_version = rows, cols, dtype, stream_version
         self._stream = torch.cuda.Stream()
         self._generated: torch.Tensor | None = None
         self._event: torch.cuda.Event | None = None
@@ -87,13 +90,13 @@ class _NormGenerator:
         self.matrix_index: int | None = None  # which matrix of the stream is in flight
 
     @classmethod
-    def create(cls, rows: int, cols: int, *, dtype: torch.dtype) -> Result["_NormGenerator", InvalidShape | InvalidDType]:
+    def create(cls, rows: int, cols: int, *, dtype: torch.dtype, stream_version: int = 0) -> Result["_NormGenerator", InvalidShape | InvalidDType]:
         if min(rows, cols) <= 0:
             return Failure(InvalidShape(rows=rows, cols=cols))
         checked = _validate_dtype(dtype)
         if isinstance(checked, Failure):
             return checked
-        return Success(cls(rows, cols, dtype=dtype))
+        return Success(cls(rows, cols, dtype=dtype, stream_version=stream_version))
 
     def enqueue(self, seed: int, matrix_index: int = 0) -> Result[None, QueueBusy | SeedOutOfRange]:
         """Launch the fill kernel for matrix ``matrix_index`` of stream ``seed`` (non-blocking)."""
@@ -104,7 +107,7 @@ class _NormGenerator:
         self._event = torch.cuda.Event()
         with torch.cuda.stream(self._stream):
             out = torch.empty((self._rows, self._cols), dtype=self._dtype, device="cuda")
-            _cabi.philox_normals(out, seed, matrix_index)
+            _cabi.philox_normals(out, seed, matrix_index, self._stream_version)
             self._event.record()
         self._generated = out
         self.matrix_index = matrix_index
@@ -145,8 +148,9 @@ class _NormGenerator:
 class ConcurrentNormGenerator:
     """Round-robin pool of workers with a deterministic ``(seed, skips)`` checkpoint."""
 
-    def __init__(self, *, pool: list[_NormGenerator], rows: int, cols: int, dtype: torch.dtype, base_seed: int, served: int) -> None:
-        self._rows, self._cols, self._dtype = rows, cols, dtype
+    def __init__(self, *, pool: list[_NormGenerator], rows: int, cols: int, dtype: torch.dtype, base_seed: int, served: int,
+                 stream_version: int = 0) -> None:
+        self._rows, self._cols, self._dtype, self._stream_version = rows, cols, dtype, stream_version
         self._base_seed = base_seed
         self._served = served
         self._pool = pool
@@ -164,7 +168,7 @@ class ConcurrentNormGenerator:
         dtype = config.dtype.to_torch()
 
         def _make(slot: int) -> Result[_NormGenerator, InvalidShape | InvalidDType | QueueBusy | SeedOutOfRange]:
-            made = _NormGenerator.create(config.rows, config.cols, dtype=dtype)
+            made = _NormGenerator.create(config.rows, config.cols, dtype=dtype, stream_version=config.stream_version)
             if isinstance(made, Failure):
                 return made
             queued = made.value.enqueue(config.seed, config.skips + slot)
@@ -175,7 +179,8 @@ class ConcurrentNormGenerator:
             return made
         # slot (k mod size) always holds matrix k
         pool = sorted(made.value, key=lambda g: (g.matrix_index or 0) % buffer.size)
-        return Success(cls(pool=pool, rows=config.rows, cols=config.cols, dtype=dtype, base_seed=config.seed, served=config.skips))
+        return Success(cls(pool=pool, rows=config.rows, cols=config.cols, dtype=dtype, base_seed=config.seed, served=config.skips,
+                           stream_version=config.stream_version))
 
     def _update_idle_state(self) -> None:
         """Accumulate wall time during which every worker's matrix is ready (reference :361-382)."""
@@ -208,7 +213,8 @@ class ConcurrentNormGenerator:
 
     def snapshot(self) -> ConcurrentNormGeneratorConfig:
         made = ConcurrentNormGeneratorConfig.create(
-            rows=self._rows, cols=self._cols, seed=self._base_seed, dtype=Precision.from_torch(self._dtype), skips=self._served
+            rows=self._rows, cols=self._cols, seed=self._base_seed, dtype=Precision.from_torch(self._dtype), skips=self._served,
+            stream_version=self._stream_version,
         )
         if isinstance(made, Failure):
             raise AssertionError(f"Invalid ConcurrentNormGeneratorConfig snapshot: {made.error}")

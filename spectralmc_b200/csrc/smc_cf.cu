@@ -33,10 +33,11 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "smc_internal.h"  // first: fixes SMC_NS / the Philox round count of this build of the file
 #include "smc_device.cuh"
-#include "smc_internal.h"
 
-namespace smc {
+namespace SMC_NS {
+using namespace ::smc;  // shared helpers (smc_internal.h); everything that draws normals lives in SMC_NS
 
 constexpr int CF_BLOCK = 256;
 constexpr int64_t TARGET_TILES = 12288;  // CTAs per launch aimed at (profiles/r2_codegen_variant_matrix.txt: 4096..24576 within 1 %)
@@ -1173,6 +1174,8 @@ static int check_args(const char* fn, const smc_fused_args* a) {
   SMC_REQUIRE(static_cast<double>(a->batches_total) * static_cast<double>(a->network_size) <= 4294967295.0,
               "%s: total paths exceed the 32-bit path counter", fn);
   SMC_REQUIRE(a->timesteps <= 0x7fffffffLL, "%s: timesteps too large", fn);
+  SMC_REQUIRE(a->stream_version == SMC_STREAM_PHILOX10 || a->stream_version == SMC_STREAM_PHILOX7, "%s: invalid stream_version %d", fn,
+              a->stream_version);
   SMC_REQUIRE((a->first_matrix_index >> 62) == 0, "%s: first_matrix_index too large", fn);
   return SMC_OK;
 }
@@ -1374,10 +1377,11 @@ static bool valid_shape(const smc_fused_args* a) {
   return a != nullptr && a->n_contracts > 0 && a->network_size > 0 && a->batch_end > a->batch_begin && a->timesteps > 0;
 }
 
-}  // namespace smc
+}  // namespace SMC_NS
 
-using namespace smc;
+using namespace SMC_NS;
 
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_cf_fused_workspace_bytes(const smc_fused_args* a) {
   if (!valid_shape(a)) return 0;
   const TilePlan plan = sim_plan(a);
@@ -1388,15 +1392,19 @@ extern "C" size_t smc_cf_fused_workspace_bytes(const smc_fused_args* a) {
   int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(a->n_contracts, static_cast<int64_t>(cap / per)));
   return per * chunk + align_up(a->n_contracts * sizeof(double)) + 256;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused_launch_count(const smc_fused_args* a) {
   if (!valid_shape(a)) return 0;
   const int separate = finalize_plan(a->network_size).in_step ? 0 : 1;
   if (a->normalization == SMC_RAW) return 1 + separate;  // the step kernel (+ the transform kernel for large N)
   return 2 + separate;  // terminal step + payoff step (+ transform), per chunk of contracts
 }
+#endif
 
 // introspection: how the simulation of these arguments is cut into CTAs (no device access)
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused_plan(const smc_fused_args* a, int64_t* out, int capacity) {
   clear_error();
   if (int e = check_args("smc_cf_fused_plan", a)) return e;
@@ -1409,6 +1417,7 @@ extern "C" int smc_cf_fused_plan(const smc_fused_args* a, int64_t* out, int capa
   out[4] = plan.tree.count[plan.tree.levels];
   return SMC_OK;
 }
+#endif
 
 template <typename Real>
 static int cf_fused_impl(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -1453,21 +1462,27 @@ static int cf_fused_impl(const smc_fused_args* a, const smc_p2p_group* g, void* 
   return SMC_OK;
 }
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused(const smc_fused_args* a, void* cf_out, void* ws, size_t ws_bytes, void* stream) {
   clear_error();
   if (int e = check_args("smc_cf_fused", a)) return e;
   SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr, "smc_cf_fused: NULL pointer");
   SMC_REQUIRE(ws != nullptr, "smc_cf_fused: workspace is NULL");
+  if (a->stream_version == SMC_STREAM_PHILOX7) return smc_p7_cf_fused(a, nullptr, cf_out, ws, ws_bytes, stream);
   return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, nullptr, cf_out, ws, ws_bytes, as_stream(stream))
                              : cf_fused_impl<double>(a, nullptr, cf_out, ws, ws_bytes, as_stream(stream));
 }
+#endif
 
 // ---- batch-sharded RAW with the all-reduce fused into the step kernel (peer memory) ----------------
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_p2p_buffer_bytes(int64_t capacity_contracts, int64_t network_size, int world) {
   if (capacity_contracts <= 0 || network_size <= 0 || world <= 0 || world > MAX_PEERS) return 0;
   return exchange_total_cells(capacity_contracts, network_size, world) * sizeof(double);
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_alloc(size_t bytes, void** ptr, void* handle64) {
   clear_error();
   SMC_REQUIRE(bytes > 0 && ptr && handle64, "smc_p2p_alloc: bad argument");
@@ -1478,7 +1493,9 @@ extern "C" int smc_p2p_alloc(size_t bytes, void** ptr, void* handle64) {
   SMC_CUDA_OK(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), *ptr));
   return SMC_OK;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_open(const void* handle64, void** ptr) {
   clear_error();
   SMC_REQUIRE(handle64 && ptr, "smc_p2p_open: bad argument");
@@ -1487,18 +1504,23 @@ extern "C" int smc_p2p_open(const void* handle64, void** ptr) {
   SMC_CUDA_OK(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
   return SMC_OK;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_close(void* ptr) {
   clear_error();
   SMC_CUDA_OK(cudaIpcCloseMemHandle(ptr));
   return SMC_OK;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_free(void* ptr) {
   clear_error();
   SMC_CUDA_OK(cudaFree(ptr));
   return SMC_OK;
 }
+#endif
 
 static int check_group_only(const char* fn, const smc_p2p_group* g) {
   SMC_REQUIRE(g != nullptr, "%s: group is NULL", fn);
@@ -1521,6 +1543,7 @@ static int check_group(const char* fn, const smc_fused_args* a, const smc_p2p_gr
 
 // Everything smc_cf_fused_p2p would reject, without touching the device: callers validate BEFORE they
 // advance the epoch, so that a host-side failure on one rank cannot put the ranks out of step.
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused_p2p_check(const smc_fused_args* a, const smc_p2p_group* g, size_t ws_bytes) {
   clear_error();
   if (int e = check_args("smc_cf_fused_p2p", a)) return e;
@@ -1533,16 +1556,21 @@ extern "C" int smc_cf_fused_p2p_check(const smc_fused_args* a, const smc_p2p_gro
   if (ws_bytes < need) return set_error(SMC_EWORKSPACE, "smc_cf_fused_p2p: workspace %zu < %zu", ws_bytes, need);
   return SMC_OK;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused_p2p(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes,
                                 void* stream) {
   if (int e = smc_cf_fused_p2p_check(a, g, ws_bytes)) return e;
   SMC_REQUIRE(a->contracts != nullptr && cf_out != nullptr && ws != nullptr, "smc_cf_fused_p2p: NULL pointer");
+  if (a->stream_version == SMC_STREAM_PHILOX7) return smc_p7_cf_fused(a, g, cf_out, ws, ws_bytes, stream);
   return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
                              : cf_fused_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
 }
+#endif
 
 // Epoch of the first call on this rank whose wait for a peer timed out (0: none).  Synchronises `stream`.
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_status(const smc_p2p_group* g, uint32_t* timed_out_epoch, void* stream) {
   clear_error();
   SMC_REQUIRE(timed_out_epoch != nullptr && g != nullptr, "smc_p2p_status: NULL pointer");
@@ -1555,12 +1583,15 @@ extern "C" int smc_p2p_status(const smc_p2p_group* g, uint32_t* timed_out_epoch,
   SMC_CUDA_OK(cudaStreamSynchronize(as_stream(stream)));
   return SMC_OK;
 }
+#endif
 
 // ---- two-phase API for batch-sharded NORMALIZE -------------------------------------------
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_fused_terminal_workspace_bytes(const smc_fused_args* a) {
   if (!valid_shape(a)) return 0;
   return terminal_step_bytes(sim_plan(a), a->n_contracts) + 256;
 }
+#endif
 
 template <typename Real>
 static int fused_terminal_impl(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
@@ -1572,19 +1603,24 @@ static int fused_terminal_impl(const smc_fused_args* a, void* terminal, double* 
   return terminal_step<Real>(base_params(a, plan), plan, a->n_contracts, terminal, terminal_sum, w, st);
 }
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_fused_terminal(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws,
                                   size_t ws_bytes, void* stream) {
   clear_error();
   if (int e = check_args("smc_fused_terminal", a)) return e;
   SMC_REQUIRE(a->contracts && terminal && terminal_sum && ws, "smc_fused_terminal: NULL pointer");
+  if (a->stream_version == SMC_STREAM_PHILOX7) return smc_p7_fused_terminal(a, terminal, terminal_sum, ws, ws_bytes, stream);
   return a->dtype == SMC_F32 ? fused_terminal_impl<float>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream))
                              : fused_terminal_impl<double>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream));
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_cf_from_terminal_workspace_bytes(const smc_fused_args* a) {
   if (!valid_shape(a)) return 0;
   return colsum_bytes(stream_plan(a), a->n_contracts, a->network_size) + 256;
 }
+#endif
 
 template <typename Real>
 static int cf_from_terminal_impl(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal, const double* tsum,
@@ -1601,6 +1637,7 @@ static int cf_from_terminal_impl(const smc_fused_args* a, const smc_p2p_group* g
   return colsum_step<Real, SRC_TERMINAL>(p, plan, a->n_contracts, n, cf_out, 0, g, w, st);
 }
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* terminal, const double* tsum, void* cf_out,
                                     void* ws, size_t ws_bytes, void* stream) {
   clear_error();
@@ -1612,9 +1649,11 @@ extern "C" int smc_cf_from_terminal(const smc_fused_args* a, const void* termina
              ? cf_from_terminal_impl<float>(a, nullptr, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
              : cf_from_terminal_impl<double>(a, nullptr, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
 }
+#endif
 
 // NORMALIZE over several GPUs without a collective call: smc_fused_terminal, then this in-place sum over
 // ranks of the per-contract terminal sums, then smc_cf_from_terminal_p2p.
+#ifndef SMC_STREAM_P7
 extern "C" int smc_p2p_allreduce_sum_f64(double* inout, int64_t count, const smc_p2p_group* g, void* stream) {
   clear_error();
   SMC_REQUIRE(inout != nullptr && count > 0, "smc_p2p_allreduce_sum_f64: bad argument");
@@ -1625,7 +1664,9 @@ extern "C" int smc_p2p_allreduce_sum_f64(double* inout, int64_t count, const smc
   SMC_LAUNCH_OK("p2p_allreduce_small_kernel");
   return SMC_OK;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_from_terminal_p2p(const smc_fused_args* a, const smc_p2p_group* g, const void* terminal,
                                         const double* tsum, void* cf_out, void* ws, size_t ws_bytes, void* stream) {
   clear_error();
@@ -1640,14 +1681,18 @@ extern "C" int smc_cf_from_terminal_p2p(const smc_fused_args* a, const smc_p2p_g
              ? cf_from_terminal_impl<float>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream))
              : cf_from_terminal_impl<double>(a, g, terminal, tsum, cf_out, ws, ws_bytes, as_stream(stream));
 }
+#endif
 
 // ---- materialised payoff matrix -> CF -------------------------------------------------------
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_cf_fft_mean_workspace_bytes(int64_t batches, int64_t n, int method) {
   if (batches <= 0 || n <= 0) return 0;
   if (method == SMC_CF_ROW_FFT && rowfft_supported(n)) return rowfft_workspace_bytes(batches, n);
   return colsum_bytes(make_plan(1, batches, n, true), 1, n) + 256;
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int dtype, int method, void* out,
                                void* ws, size_t ws_bytes, void* stream) {
   clear_error();
@@ -1676,8 +1721,10 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   if (dtype == SMC_F32) return colsum_step<float, SRC_MATRIX>(p, plan, 1, n, out, 0, nullptr, w, st);
   return colsum_step<double, SRC_MATRIX>(p, plan, 1, n, out, 0, nullptr, w, st);
 }
+#endif
 
 // ---- per-row spectra (the ComputeFFT operator) ----------------------------------------------
+#ifndef SMC_STREAM_P7
 extern "C" int smc_fft_rows(const void* mat, int64_t batches, int64_t n, int dtype, void* out, void* stream) {
   clear_error();
   SMC_REQUIRE(batches > 0 && n > 0, "smc_fft_rows: invalid shape (%lld, %lld)", (long long)batches, (long long)n);
@@ -1685,15 +1732,19 @@ extern "C" int smc_fft_rows(const void* mat, int64_t batches, int64_t n, int dty
   SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_fft_rows: invalid dtype %d", dtype);
   return fft_rows(mat, batches, n, dtype, out, as_stream(stream));
 }
+#endif
 
 // ---- host-buffer entry point ----------------------------------------------------------------
+#ifndef SMC_STREAM_P7
 extern "C" size_t smc_cf_fused_host_workspace_bytes(const smc_fused_args* a) {
   if (a == nullptr || a->n_contracts <= 0) return 0;
   const size_t cbytes = align_up(static_cast<size_t>(a->n_contracts) * 6 * sizeof(double));
   const size_t obytes = align_up(static_cast<size_t>(a->n_contracts) * a->network_size * 2 * real_size(a->dtype));
   return cbytes + obytes + smc_cf_fused_workspace_bytes(a);
 }
+#endif
 
+#ifndef SMC_STREAM_P7
 extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contracts_host, void* cf_host, void* ws,
                                  size_t ws_bytes, void* stream) {
   clear_error();
@@ -1731,3 +1782,17 @@ extern "C" int smc_cf_fused_host(const smc_fused_args* a, const double* contract
   SMC_CUDA_OK(cudaStreamSynchronize(st));
   return SMC_OK;
 }
+#endif
+
+// ---- the Philox4x32-7 build of this file exports only the two entry points that draw normals -------------
+#ifdef SMC_STREAM_P7
+extern "C" int smc_p7_cf_fused(const smc_fused_args* a, const smc_p2p_group* g, void* cf_out, void* ws, size_t ws_bytes, void* stream) {
+  return a->dtype == SMC_F32 ? cf_fused_impl<float>(a, g, cf_out, ws, ws_bytes, as_stream(stream))
+                             : cf_fused_impl<double>(a, g, cf_out, ws, ws_bytes, as_stream(stream));
+}
+extern "C" int smc_p7_fused_terminal(const smc_fused_args* a, void* terminal, double* terminal_sum, void* ws, size_t ws_bytes,
+                                     void* stream) {
+  return a->dtype == SMC_F32 ? fused_terminal_impl<float>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream))
+                             : fused_terminal_impl<double>(a, terminal, terminal_sum, ws, ws_bytes, as_stream(stream));
+}
+#endif

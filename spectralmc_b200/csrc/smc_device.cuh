@@ -8,7 +8,11 @@
 
 #include <cstdint>
 
-namespace smc {
+#ifndef SMC_NS
+#define SMC_NS smc
+#endif
+
+namespace SMC_NS {
 
 constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
 constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
@@ -40,7 +44,7 @@ inline PhiloxKeys make_philox_keys(uint64_t seed) {
 // word that changes inside a path's time loop; it sits in an XOR slot so that both first-round
 // products and one second-round product are loop-invariant (17 IMAD.WIDE per block, not 20).
 #ifndef SMC_PHILOX_ROUNDS
-#define SMC_PHILOX_ROUNDS 10  // EVALUATION builds only (profiles/r2_philox7_evaluation.md): the shipped stream is Philox4x32-10
+#define SMC_PHILOX_ROUNDS 10  // 7 in the -DSMC_STREAM_P7 build of the stream-drawing translation units (smc_internal.h)
 #endif
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                               const PhiloxKeys& key, uint32_t (&out)[4]) {
@@ -457,4 +461,4 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
   return t;
 }
 
-}  // namespace smc
+}  // namespace SMC_NS

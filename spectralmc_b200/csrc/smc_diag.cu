@@ -9,10 +9,11 @@
 //                                the 6-row blocks) and z[i, j] z[i, j + 1] across adjacent columns
 // Test infrastructure in the sense that only tests/test_gpu_stream_battery.py calls it; it reuses the very device
 // functions the path kernels draw their normals with (smc_device.cuh), which is the point.
+#include "smc_internal.h"  // first: fixes SMC_NS / the Philox round count of this build of the file
 #include "smc_device.cuh"
-#include "smc_internal.h"
 
-namespace smc {
+namespace SMC_NS {
+using namespace ::smc;  // shared helpers (smc_internal.h); everything that draws normals lives in SMC_NS
 
 constexpr int DIAG_BLOCK = 256;
 
@@ -106,17 +107,9 @@ __global__ void __launch_bounds__(DIAG_BLOCK)
   }
 }
 
-}  // namespace smc
-
-using namespace smc;
-
-extern "C" int smc_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols,
-                                          uint32_t* radius_hist, uint32_t* angle_hist, uint64_t* tails4, double* power_sums4,
-                                          void* stream) {
-  clear_error();
-  SMC_REQUIRE(radius_hist && angle_hist && tails4 && power_sums4, "smc_diag_stream_fields_f32: NULL pointer");
-  SMC_REQUIRE(n_blocks > 0 && cols > 0 && n_blocks / cols < 0x40000000ull, "smc_diag_stream_fields_f32: bad shape");
-  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_diag_stream_fields_f32: matrix_index must be < 2^63");
+// the launches, in this build's namespace (Philox4x32-10 in the plain build, -7 under SMC_STREAM_P7)
+static int launch_fields(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols, uint32_t* radius_hist,
+                         uint32_t* angle_hist, uint64_t* tails4, double* power_sums4, void* stream) {
   const int sms = sm_count();
   SMC_REQUIRE(sms > 0, "smc_diag_stream_fields_f32: no CUDA device");
   diag_fields_kernel<<<static_cast<unsigned>(sms) * 8u, DIAG_BLOCK, 0, as_stream(stream)>>>(
@@ -126,14 +119,49 @@ extern "C" int smc_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, 
   return SMC_OK;
 }
 
-extern "C" int smc_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7,
-                                        void* stream) {
-  clear_error();
-  SMC_REQUIRE(sums7 != nullptr, "smc_diag_stream_lags_f32: NULL pointer");
-  SMC_REQUIRE(cols > 0 && rows >= 12 && rows % 6 == 0, "smc_diag_stream_lags_f32: rows must be a multiple of 6, at least 12");
-  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_diag_stream_lags_f32: matrix_index must be < 2^63");
+static int launch_lags(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7, void* stream) {
   diag_lags_kernel<<<(cols + DIAG_BLOCK - 1) / DIAG_BLOCK, DIAG_BLOCK, 0, as_stream(stream)>>>(
       make_philox_keys(seed), static_cast<uint32_t>(matrix_index), static_cast<uint32_t>(matrix_index >> 32), cols, rows / 6, sums7);
   SMC_LAUNCH_OK("diag_lags_kernel");
   return SMC_OK;
 }
+
+}  // namespace SMC_NS
+
+using namespace SMC_NS;
+
+#ifdef SMC_STREAM_P7
+extern "C" int smc_p7_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols,
+                                             uint32_t* radius_hist, uint32_t* angle_hist, uint64_t* tails4, double* power_sums4,
+                                             void* stream) {
+  return launch_fields(seed, matrix_index, n_blocks, cols, radius_hist, angle_hist, tails4, power_sums4, stream);
+}
+extern "C" int smc_p7_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7,
+                                           void* stream) {
+  return launch_lags(seed, matrix_index, cols, rows, sums7, stream);
+}
+#else
+extern "C" int smc_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols,
+                                          uint32_t* radius_hist, uint32_t* angle_hist, uint64_t* tails4, double* power_sums4,
+                                          int stream_version, void* stream) {
+  clear_error();
+  SMC_REQUIRE(radius_hist && angle_hist && tails4 && power_sums4, "smc_diag_stream_fields_f32: NULL pointer");
+  SMC_REQUIRE(n_blocks > 0 && cols > 0 && n_blocks / cols < 0x40000000ull, "smc_diag_stream_fields_f32: bad shape");
+  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_diag_stream_fields_f32: matrix_index must be < 2^63");
+  SMC_REQUIRE(stream_version == SMC_STREAM_PHILOX10 || stream_version == SMC_STREAM_PHILOX7, "smc_diag_stream_fields_f32: invalid stream_version %d", stream_version);
+  if (stream_version == SMC_STREAM_PHILOX7)
+    return smc_p7_diag_stream_fields_f32(seed, matrix_index, n_blocks, cols, radius_hist, angle_hist, tails4, power_sums4, stream);
+  return launch_fields(seed, matrix_index, n_blocks, cols, radius_hist, angle_hist, tails4, power_sums4, stream);
+}
+
+extern "C" int smc_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7,
+                                        int stream_version, void* stream) {
+  clear_error();
+  SMC_REQUIRE(sums7 != nullptr, "smc_diag_stream_lags_f32: NULL pointer");
+  SMC_REQUIRE(cols > 0 && rows >= 12 && rows % 6 == 0, "smc_diag_stream_lags_f32: rows must be a multiple of 6, at least 12");
+  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_diag_stream_lags_f32: matrix_index must be < 2^63");
+  SMC_REQUIRE(stream_version == SMC_STREAM_PHILOX10 || stream_version == SMC_STREAM_PHILOX7, "smc_diag_stream_lags_f32: invalid stream_version %d", stream_version);
+  if (stream_version == SMC_STREAM_PHILOX7) return smc_p7_diag_stream_lags_f32(seed, matrix_index, cols, rows, sums7, stream);
+  return launch_lags(seed, matrix_index, cols, rows, sums7, stream);
+}
+#endif

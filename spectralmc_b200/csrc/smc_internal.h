@@ -9,6 +9,32 @@
 
 #include "spectralmc_b200.h"
 
+// ---- stream variants ------------------------------------------------------------------------------
+// The translation units that draw normals (smc_normals.cu, smc_cf.cu, smc_diag.cu) are compiled TWICE:
+// once as they are (Philox4x32-10, namespace smc, the exported smc_* entry points) and once with
+// -DSMC_STREAM_P7 (Philox4x32-7, namespace smc_p7, three internal entry points smc_p7_*) — the round count has
+// to be a compile-time constant for the round keys to stay constant-bank operands, and a second namespace
+// keeps the two sets of kernels apart at link time.  The exported entry points dispatch on
+// `stream_version` (SMC_STREAM_PHILOX10 / SMC_STREAM_PHILOX7).  smc_device.cuh follows SMC_NS.
+#ifdef SMC_STREAM_P7
+#define SMC_NS smc_p7
+#define SMC_PHILOX_ROUNDS 7
+#else
+#define SMC_NS smc
+#endif
+
+#define SMC_INTERNAL __attribute__((visibility("hidden")))
+extern "C" {
+SMC_INTERNAL int smc_p7_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed, uint64_t matrix_index, void* stream);
+SMC_INTERNAL int smc_p7_cf_fused(const smc_fused_args* args, const smc_p2p_group* group, void* cf_out, void* workspace, size_t workspace_bytes,
+                    void* stream);
+SMC_INTERNAL int smc_p7_fused_terminal(const smc_fused_args* args, void* terminal, double* terminal_sum, void* workspace,
+                          size_t workspace_bytes, void* stream);
+SMC_INTERNAL int smc_p7_diag_stream_fields_f32(uint64_t seed, uint64_t matrix_index, uint64_t n_blocks, uint32_t cols, uint32_t* radius_hist,
+                                  uint32_t* angle_hist, uint64_t* tails4, double* power_sums4, void* stream);
+SMC_INTERNAL int smc_p7_diag_stream_lags_f32(uint64_t seed, uint64_t matrix_index, uint32_t cols, uint32_t rows, double* sums7, void* stream);
+}
+
 namespace smc {
 
 // thread-local message behind smc_last_error()

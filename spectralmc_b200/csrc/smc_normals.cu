@@ -9,10 +9,11 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include "smc_internal.h"  // first: fixes SMC_NS / the Philox round count of this build of the file
 #include "smc_device.cuh"
-#include "smc_internal.h"
 
-namespace smc {
+namespace SMC_NS {
+using namespace ::smc;  // shared helpers (smc_internal.h)
 
 constexpr int NORMALS_BLOCK = 256;
 constexpr int GROUPS_PER_THREAD = 4;  // row groups walked by one thread (24 rows f32 / 8 rows f64)
@@ -133,20 +134,8 @@ __global__ void __launch_bounds__(NORMALS_BLOCK)
   }
 }
 
-}  // namespace smc
-
-using namespace smc;
-
-extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
-                                  uint64_t matrix_index, void* stream) {
-  clear_error();
-  SMC_REQUIRE(rows > 0 && cols > 0, "smc_philox_normals: invalid shape (%lld, %lld)", (long long)rows,
-              (long long)cols);
-  SMC_REQUIRE(out != nullptr, "smc_philox_normals: out is NULL");
-  SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_philox_normals: invalid dtype %d", dtype);
-  SMC_REQUIRE(cols <= 0xffffffffLL, "smc_philox_normals: cols %lld exceeds the 32-bit path counter",
-              (long long)cols);
-  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_philox_normals: matrix_index must be < 2^63");
+// argument-checked launch, in this build's namespace (Philox4x32-10 in the plain build, -7 under SMC_STREAM_P7)
+static int launch_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed, uint64_t matrix_index, void* stream) {
   const PhiloxKeys key = make_philox_keys(seed);
   const uint32_t k_lo = static_cast<uint32_t>(matrix_index);
   const uint32_t k_hi = static_cast<uint32_t>(matrix_index >> 32);
@@ -196,3 +185,34 @@ extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dty
   SMC_LAUNCH_OK("philox_normals_kernel");
   return SMC_OK;
 }
+
+}  // namespace SMC_NS
+
+using namespace SMC_NS;
+
+#ifdef SMC_STREAM_P7
+extern "C" int smc_p7_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed, uint64_t matrix_index,
+                                     void* stream) {
+  return launch_normals(out, rows, cols, dtype, seed, matrix_index, stream);
+}
+#else
+extern "C" int smc_philox_normals_v(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
+                                    uint64_t matrix_index, int stream_version, void* stream) {
+  clear_error();
+  SMC_REQUIRE(rows > 0 && cols > 0, "smc_philox_normals: invalid shape (%lld, %lld)", (long long)rows,
+              (long long)cols);
+  SMC_REQUIRE(out != nullptr, "smc_philox_normals: out is NULL");
+  SMC_REQUIRE(dtype == SMC_F32 || dtype == SMC_F64, "smc_philox_normals: invalid dtype %d", dtype);
+  SMC_REQUIRE(cols <= 0xffffffffLL, "smc_philox_normals: cols %lld exceeds the 32-bit path counter",
+              (long long)cols);
+  SMC_REQUIRE((matrix_index >> 63) == 0, "smc_philox_normals: matrix_index must be < 2^63");
+  SMC_REQUIRE(stream_version == SMC_STREAM_PHILOX10 || stream_version == SMC_STREAM_PHILOX7, "smc_philox_normals: invalid stream_version %d", stream_version);
+  if (stream_version == SMC_STREAM_PHILOX7) return smc_p7_philox_normals(out, rows, cols, dtype, seed, matrix_index, stream);
+  return launch_normals(out, rows, cols, dtype, seed, matrix_index, stream);
+}
+
+extern "C" int smc_philox_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t seed,
+                                  uint64_t matrix_index, void* stream) {
+  return smc_philox_normals_v(out, rows, cols, dtype, seed, matrix_index, SMC_STREAM_PHILOX10, stream);
+}
+#endif

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol() -> None:
 def test_version_and_error_string() -> None:
     from spectralmc_b200 import _cabi
 
-    assert _cabi.version() == 101
+    assert _cabi.version() == 102
     assert isinstance(_cabi.LIB.smc_last_error(), bytes)
 
 
@@ -141,3 +141,14 @@ def test_tile_plan_depends_on_the_problem_shape_only() -> None:
     assert _cabi.LIB.smc_cf_fused_launch_count(ctypes.byref(c2)) == 1  # the RAW step is ONE kernel
     c2.normalization = _cabi.SMC_NORMALIZE
     assert _cabi.LIB.smc_cf_fused_launch_count(ctypes.byref(c2)) == 2
+
+
+def test_stream_version_is_validated_without_a_device() -> None:
+    from spectralmc_b200 import _cabi
+
+    torch = __import__("torch")
+    args = _cabi.make_fused_args(None, 1, 12, 16, 64, torch.float32, 0, _cabi.SMC_RAW, 42, 0, stream_version=2)
+    args.contracts = 16
+    assert _cabi.LIB.smc_cf_fused(ctypes.byref(args), 16, 16, 1 << 20, None) == 1 and b"stream_version" in _cabi.LIB.smc_last_error()
+    assert _cabi.LIB.smc_philox_normals_v(16, 4, 4, 0, 1, 0, 5, None) == 1 and b"stream_version" in _cabi.LIB.smc_last_error()
+    assert _cabi.make_fused_args(None, 1, 12, 16, 64, torch.float32, 0, _cabi.SMC_RAW, 42, 0).stream_version == _cabi.SMC_STREAM_PHILOX10

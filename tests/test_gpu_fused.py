@@ -34,10 +34,10 @@ CANON = (100.0, 100.0, 1.0, 0.05, 0.0, 0.2)
 ODD = (37.5, 41.0, 2.5, -0.01, 0.03, 0.65)
 
 
-def _oracle_cf(rows, T, N, B, np_dtype, seed, first_index, scheme, norm):
+def _oracle_cf(rows, T, N, B, np_dtype, seed, first_index, scheme, norm, stream_version=0):
     out = []
     for i, row in enumerate(rows):
-        z = philox.normals_matrix(T, N * B, np_dtype, seed, first_index + i)
+        z = philox.normals_matrix(T, N * B, np_dtype, seed, first_index + i, stream_version=stream_version)
         cf, _ = ogbm.simulate_fft(ogbm.Contract(*row), z, N, scheme=scheme, normalization=norm)
         out.append(np.asarray(cf, dtype=np.complex128))
     return np.stack(out)
@@ -108,6 +108,44 @@ def test_short_paths_shard_at_any_row(cuts) -> None:
     total = sum(_fused([CANON, ODD], T, N, B, torch.float32, 5, 0, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, batch_begin=lo, batch_end=hi)
                 for lo, hi in zip(cuts[:-1], cuts[1:]))
     assert rel_max(total, whole) <= 2e-6
+
+
+@pytest.mark.parametrize("T,N,B", [(12, 16, 64), (252, 128, 16), (1, 16, 100), (3, 32, 50), (7, 12, 11)])
+@pytest.mark.parametrize("norm", ["raw_paths", "normalize_forwards"])
+@pytest.mark.parametrize("prec", ["float64", "float32"])
+def test_opt_in_philox7_stream_through_the_fused_path(T, N, B, norm, prec) -> None:
+    """stream_version 1: the fused kernels (a second build of the same translation unit with seven Philox rounds)
+    against the oracle's statement of that stream; and the default stream is untouched by its presence."""
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    rows = [CANON, ODD]
+    contracts = torch.tensor(np.asarray(rows, dtype=np.float64), device="cuda")
+    code = _cabi.SMC_NORMALIZE if norm == "normalize_forwards" else _cabi.SMC_RAW
+    args = _cabi.make_fused_args(contracts, 2, T, N, B, dtype, _cabi.SMC_LOG_EULER, code, 42, 5, stream_version=_cabi.SMC_STREAM_PHILOX7)
+    got = _cabi.cf_fused(args, contracts.device, dtype).cpu().numpy()
+    ref = _oracle_cf(rows, T, N, B, np.dtype(prec), 42, 5, "log_euler", norm, stream_version=1)
+    tol = 1e-12 if prec == "float64" else 1e-5
+    for c in range(2):
+        assert rel_max(got[c], ref[c]) <= tol, (c, rel_max(got[c], ref[c]))
+    default = _fused(rows, T, N, B, dtype, 42, 5, _cabi.SMC_LOG_EULER, code)
+    assert rel_max(default, _oracle_cf(rows, T, N, B, np.dtype(prec), 42, 5, "log_euler", norm)) <= tol
+    assert rel_max(got, default) > 1e-4  # a different sample set
+
+
+def test_opt_in_stream_through_the_engine_api() -> None:
+    """SimulationParams(stream_version=1) selects it end to end: fused targets, the materialised generator, snapshots."""
+    sp7 = make_simulation_params(timesteps=6, network_size=16, batches_per_mc_run=64, mc_seed=9, dtype=Precision.float32).model_copy(
+        update={"stream_version": 1})
+    cfg = make_black_scholes_config(sim_params=sp7, path_scheme=PathScheme.LOG_EULER, normalization=ForwardNormalization.RAW)
+    engine = BlackScholes(cfg)
+    contract = BlackScholes.Inputs(X0=CANON[0], K=CANON[1], T=CANON[2], r=CANON[3], d=CANON[4], v=CANON[5])
+    fused = expect_success(engine.cf_targets([contract]))[0].cpu().numpy()
+    ref = _oracle_cf([CANON], 6, 16, 64, np.dtype("float32"), 9, 0, "log_euler", "raw_paths", stream_version=1)[0]
+    assert rel_max(fused, ref) <= 1e-5
+    sims = expect_success(engine._simulate(contract)).sims.cpu().numpy()  # matrix 1 of the stream, materialised
+    z = philox.normals_matrix(6, 16 * 64, np.float32, 9, 1, stream_version=1)
+    ogbm.simulate_paths_inplace(z, 6, CANON[2] / 6, CANON[0], CANON[3], CANON[4], CANON[5], True)
+    assert rel_max(sims, z) <= 2e-5
+    assert expect_success(engine.snapshot()).sim_params.stream_version == 1
 
 
 @pytest.mark.parametrize("prec", ["float64", "float32"])

@@ -206,3 +206,21 @@ def test_uniformity_of_the_sum_over_a_path() -> None:
     s = (out.double().sum(dim=0) / T**0.5).cpu().numpy()
     assert stats.kstest(s, "norm").pvalue > 1e-3
     assert abs(s.std() - 1) < 5 / (2 * P) ** 0.5
+
+
+@pytest.mark.parametrize("rows,cols", [(12, 1024), (7, 132), (1, 1001), (3, 4097), (252, 512)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_opt_in_philox7_stream_matches_its_specification(rows, cols, dtype) -> None:
+    """stream_version 1 (Philox4x32-7, an explicit opt-in): the generator follows oracle/philox.py's statement of it,
+    in both layouts and both precisions, and differs from the default stream."""
+    np_dtype = np.float32 if dtype == torch.float32 else np.float64
+    out = torch.empty((rows, cols), dtype=dtype, device="cuda")
+    _cabi.philox_normals(out, 42, 3, _cabi.SMC_STREAM_PHILOX7)
+    got = out.cpu().numpy().astype(np.float64)
+    ref, rad = philox.normals_matrix(rows, cols, np_dtype, 42, 3, return_radius=True, stream_version=1)
+    if dtype == torch.float64:
+        assert np.max(np.abs(got - ref)) <= 1e-13
+    else:
+        tol = 2e-6 * (1 + np.abs(ref)) + 6e-7 * rad + 4e-7 / np.maximum(rad, 1e-6)
+        assert np.all(np.abs(got - ref.astype(np.float64)) <= tol)
+    assert not np.allclose(got, _device_matrix(rows, cols, dtype, 42, 3), atol=1e-3)

@@ -31,24 +31,25 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda", 0)
 
 
-def test_audit_kernels_follow_the_specification() -> None:
+@pytest.mark.parametrize("stream_version", [0, 1])
+def test_audit_kernels_follow_the_specification(stream_version) -> None:
     """Small enough for the oracle: every field count and the power sums must match it exactly / to rounding."""
     cols, groups, seed, k = 64, 40, 42, 3
-    got = _cabi.diag_stream_fields(seed, k, cols * groups, cols, DEV)
+    got = _cabi.diag_stream_fields(seed, k, cols * groups, cols, DEV, stream_version=stream_version)
     j = np.arange(cols, dtype=np.uint32)[None, :]
     q = np.arange(groups, dtype=np.uint32)[:, None]
-    x = philox.philox4x32_10((j, q, k, 0), (seed, 0))
+    x = philox.philox4x32_10((j, q, k, 0), (seed, 0), philox.STREAM_ROUNDS[stream_version])
     radius, angle = philox.f32_fields(*x)
     want_r = np.bincount(np.concatenate([r.ravel() for r in radius]).astype(np.int64), minlength=1 << 21)
     want_a = np.bincount(np.concatenate([a.ravel() for a in angle]).astype(np.int64), minlength=1 << 21)
     assert np.array_equal(got["radius_hist"].cpu().numpy(), want_r)
     assert np.array_equal(got["angle_hist"].cpu().numpy(), want_a)
-    z = philox.normals_matrix(6 * groups, cols, np.float32, seed, k).astype(np.float64)
+    z = philox.normals_matrix(6 * groups, cols, np.float32, seed, k, stream_version=stream_version).astype(np.float64)
     sums = got["power_sums"].cpu().numpy()
     for p in range(4):
         assert abs(sums[p] - np.sum(z ** (p + 1))) <= 2e-4 * np.sum(np.abs(z) ** (p + 1))
     assert got["tails"].cpu().tolist() == [int(np.sum(np.abs(z) > t)) for t in (4.0, 5.0, 5.5, 6.0)]
-    lags = _cabi.diag_stream_lags(seed, k, cols, 6 * groups, DEV).cpu().numpy()
+    lags = _cabi.diag_stream_lags(seed, k, cols, 6 * groups, DEV, stream_version=stream_version).cpu().numpy()
     for lag in range(1, 7):
         assert abs(lags[lag - 1] - np.sum(z[lag:] * z[:-lag])) <= 1e-3 * (1 + abs(np.sum(z[lag:] * z[:-lag])))
     pairs = np.arange(cols - 1)
@@ -71,10 +72,11 @@ def _spec_tail_probability(t: float) -> float:
     return float(grid + refined)
 
 
-@pytest.fixture(scope="module")
-def big_audit():
+# every statistic below runs on the default stream (Philox4x32-10) AND on the opt-in one (Philox4x32-7)
+@pytest.fixture(scope="module", params=[0, 1], ids=["philox10", "philox7"])
+def big_audit(request):
     n_blocks = (1 << 33) // 3 + 1  # 2^33 draws of each field type, 1.7e10 normals
-    out = _cabi.diag_stream_fields(20260318, 5, n_blocks, 1 << 22, DEV)
+    out = _cabi.diag_stream_fields(20260318, 5, n_blocks, 1 << 22, DEV, stream_version=request.param)
     torch.cuda.synchronize()
     return n_blocks, {k: v.cpu().numpy() for k, v in out.items()}
 
@@ -110,9 +112,10 @@ def test_tail_mass_and_moments(big_audit) -> None:
     assert abs(s4 - 3.0) < 5 * math.sqrt(96 / n) + 2e-5
 
 
-def test_no_serial_or_cross_column_correlation() -> None:
+@pytest.mark.parametrize("stream_version", [0, 1])
+def test_no_serial_or_cross_column_correlation(stream_version) -> None:
     cols, rows = 1 << 17, 1536
-    sums = _cabi.diag_stream_lags(99, 1, cols, rows, DEV).cpu().numpy()
+    sums = _cabi.diag_stream_lags(99, 1, cols, rows, DEV, stream_version=stream_version).cpu().numpy()
     for lag in range(1, 7):
         count = cols * (rows - lag)
         assert abs(sums[lag - 1] / count) < 5 / math.sqrt(count), (lag, sums[lag - 1] / count)
@@ -132,8 +135,9 @@ def _put_moments(F: float, K: float, sigma: float, df: float) -> tuple[float, fl
     return df * m1, df * math.sqrt(max(m2 - m1 * m1, 0.0))
 
 
+@pytest.mark.parametrize("stream_version", [0, 1])
 @pytest.mark.parametrize("strike_ratio", [0.5, 2.0])
-def test_deep_out_of_the_money_prices(strike_ratio) -> None:
+def test_deep_out_of_the_money_prices(strike_ratio, stream_version) -> None:
     """2^31 paths, v = 0.2, T = 1: the put with K / X0 = 0.5 lives entirely in the left tail of the terminal
     distribution (3.6 sigma and beyond), the one with K / X0 = 2 in the bulk; both streams must price both within
     4 standard errors of Black-76."""
@@ -147,7 +151,7 @@ def test_deep_out_of_the_money_prices(strike_ratio) -> None:
     se = sd / math.sqrt(N * B)
     prices = {}
     for dtype in (torch.float32, torch.float64):
-        args = _cabi.make_fused_args(contracts, 1, T, N, B, dtype, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 31, 0)
+        args = _cabi.make_fused_args(contracts, 1, T, N, B, dtype, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 31, 0, stream_version=stream_version)
         cf = _cabi.cf_fused(args, DEV, dtype)
         prices[dtype] = float(cf[0, 0].real) / N  # DC bin = N * mean put price
         # float32 path arithmetic adds a relative ~1e-7 bias to every payoff: far below one standard error here

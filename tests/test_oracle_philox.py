@@ -187,3 +187,24 @@ def test_short_layout_slices_statistics_and_c_port(rows) -> None:
     blocks = z[:, : cols // G * G].reshape(rows, -1, G).transpose(1, 2, 0).reshape(-1, 6).astype(np.float64)
     c = np.corrcoef(blocks.T)
     assert np.max(np.abs(c - np.eye(6))) < 6 / np.sqrt(blocks.shape[0])
+
+
+def test_opt_in_stream_is_the_same_construction_on_seven_rounds() -> None:
+    """stream_version 1 = Philox4x32-7.  The round count is pinned through the 10-round known answers: three more rounds
+    (with the Weyl-advanced key) applied to the 7-round output must give the 10-round output."""
+    rng = np.random.default_rng(3)
+    ctr = [rng.integers(0, 2**32, 64, dtype=np.uint64).astype(np.uint32) for _ in range(4)]
+    key = (0x243F6A88, 0x85A308D3)
+    seven = philox.philox4x32_10(ctr, key, 7)
+    advanced = ((key[0] + 7 * philox.W0) & 0xFFFFFFFF, (key[1] + 7 * philox.W1) & 0xFFFFFFFF)
+    ten = philox.philox4x32_10(seven, advanced, 3)
+    for a, b in zip(ten, philox.philox4x32_10(ctr, key)):
+        assert np.array_equal(a, b)
+    for dtype in (np.float32, np.float64):
+        for rows in (1, 3, 7, 12):
+            z10 = philox.normals_matrix(rows, 33, dtype, 5, 2)
+            z7 = philox.normals_matrix(rows, 33, dtype, 5, 2, stream_version=1)
+            assert z7.shape == z10.shape and not np.array_equal(z7, z10)
+            assert np.array_equal(z7[:, 4:20], philox.normals_matrix(rows, 33, dtype, 5, 2, col_begin=4, col_end=20, stream_version=1))
+    z = philox.normals_matrix(64, 8192, np.float32, 7, 3, stream_version=1).astype(np.float64).ravel()
+    assert abs(z.mean()) < 5 / np.sqrt(z.size) and abs(z.var() - 1) < 5 * np.sqrt(2 / z.size)

@@ -18,7 +18,7 @@ lib = ctypes.CDLL(LIBP)
 class FusedArgs(Structure):
     _fields_ = [("contracts", c_void_p), ("n_contracts", c_int64), ("timesteps", c_int64), ("network_size", c_int64),
                 ("batches_total", c_int64), ("batch_begin", c_int64), ("batch_end", c_int64), ("dtype", c_int), ("scheme", c_int),
-                ("normalization", c_int), ("seed", c_uint64), ("first_matrix_index", c_uint64)]
+                ("normalization", c_int), ("seed", c_uint64), ("first_matrix_index", c_uint64), ("stream_version", c_int)]
 
 
 lib.smc_cf_fused_workspace_bytes.restype = c_size_t
@@ -39,7 +39,8 @@ def run(name: str) -> dict:
     dev = torch.device("cuda", 0)
     rows = torch.tensor([(100.0, 100.0 + 0.01 * i, 1.0, 0.05, 0.0, 0.2) for i in range(C)], dtype=torch.float64, device=dev)
     norm = 0 if os.environ.get("SMC_NORM") == "1" else 1
-    a = FusedArgs(rows.data_ptr(), C, T, N, B, 0, B, 0 if dt == "f32" else 1, int(os.environ.get("SMC_SCHEME", "0")), norm, 7, 0)
+    a = FusedArgs(rows.data_ptr(), C, T, N, B, 0, B, 0 if dt == "f32" else 1, int(os.environ.get("SMC_SCHEME", "0")), norm, 7, 0,
+                  int(os.environ.get("SMC_STREAM", "0")))  # builds older than ABI 102 ignore the trailing field
     ws = torch.empty(lib.smc_cf_fused_workspace_bytes(byref(a)) + 256, dtype=torch.uint8, device=dev)
     out = torch.empty((C, N), dtype=torch.complex64 if dt == "f32" else torch.complex128, device=dev)
     st = torch.cuda.current_stream().cuda_stream

@@ -9,6 +9,9 @@ tmp=$(mktemp -d)
 for f in smc_api smc_normals smc_paths smc_cf smc_rowfft smc_cvnn smc_diag; do
   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v -I../../include "$@" -c $f.cu -o $tmp/$f.o 2> $tmp/$f.log &
 done
+for f in smc_normals smc_cf smc_diag; do  # the Philox4x32-7 build of the stream-drawing translation units
+  nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -I../../include -DSMC_STREAM_P7 "$@" -c $f.cu -o $tmp/$f.p7.o 2> $tmp/$f.p7.log &
+done
 wait
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $out $tmp/*.o -lcudart
 grep -A1 "tile_kernelIfLi0ELi0ELi0ELb0" $tmp/smc_cf.log | grep -E "registers|spill" | head -3
