@@ -6,7 +6,8 @@
  *
  * Each function cites the reference lines it follows (/root/reference/src/spectralmc/...).
  * The normal stream is the NEW counter-based stream specified in oracle/philox.py (the
- * reference's CuPy XORWOW draws, async_normals.py:214-215, are third-party and unpinned).
+ * reference's CuPy XORWOW draws, async_normals.py:214-215, are third-party and unpinned); this file
+ * states the DEFAULT stream (Philox4x32-10) only — the opt-in seven-round stream is stated in philox.py.
  *
  * Build: make -C oracle   ->  oracle/_build/libgbm_oracle.so   (plain C, no OpenMP: callers
  * parallelise over path ranges with threads — ctypes releases the GIL — see oracle/cport.py)
