@@ -193,8 +193,9 @@ int smc_cf_fused_launch_count(const smc_fused_args* args);
 int smc_cf_fused(const smc_fused_args* args, void* cf_out /* [n_contracts, N] complex */,
                  void* workspace, size_t workspace_bytes, void* stream);
 /* Introspection (no device access): how the simulation of `args` is cut into CTAs.
- * out = { tiles per contract, batch rows per tile, row lanes R, reduction-tree levels, fan-in of the root };
- * capacity >= 5.  The cut depends on the problem shape only, so results never depend on the device the job
+ * out = { tiles per contract, batch rows per tile, row lanes R, reduction-tree levels, fan-in of the root,
+ *         main tiles (the first `main tiles` tiles have `batch rows per tile` rows; the remaining ones, the fine tail a
+ *         single-contract launch ends on, have `tail rows per tile`), tail rows per tile }; capacity >= 7.  The cut depends on the problem shape only, so results never depend on the device the job
  * lands on. */
 int smc_cf_fused_plan(const smc_fused_args* args, int64_t* out, int capacity);
 

@@ -467,7 +467,8 @@ def cf_fused_plan(args: FusedArgs) -> dict:
     """How the simulation of ``args`` is cut into CTAs (``smc_cf_fused_plan``; no device access)."""
     out = (c_int64 * 8)()
     check(LIB.smc_cf_fused_plan(byref(args), out, 8))
-    return {"tiles": int(out[0]), "tile_rows": int(out[1]), "row_lanes": int(out[2]), "levels": int(out[3]), "root_fan_in": int(out[4])}
+    return {"tiles": int(out[0]), "tile_rows": int(out[1]), "row_lanes": int(out[2]), "levels": int(out[3]), "root_fan_in": int(out[4]),
+            "main_tiles": int(out[5]), "tail_tile_rows": int(out[6])}
 
 
 def cf_fused_host_workspace_bytes(args: FusedArgs) -> int:

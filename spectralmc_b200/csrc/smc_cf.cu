@@ -42,6 +42,8 @@ using namespace ::smc;  // shared helpers (smc_internal.h); everything that draw
 constexpr int CF_BLOCK = 256;
 constexpr int64_t TARGET_TILES = 12288;  // CTAs per launch aimed at (profiles/r2_codegen_variant_matrix.txt: 4096..24576 within 1 %)
 constexpr int64_t STREAM_TILES = 2368;  // 16 x 148
+constexpr int64_t TAIL_TILES = 2048;    // single-contract launches end on this many smallest-size tiles (about two waves)
+constexpr int64_t TARGET_TILES_FINE_TAIL = 3072;  // ... which lets their main tiles be four times larger (profiles/r2_codegen_variant_matrix.txt)
 constexpr int64_t MIN_TILE_PATH_STEPS = 16384;  // a simulated tile is at least 64 path-steps per thread
 constexpr int TREE_RADIX = 16;
 constexpr int MAX_LEVELS = 8;           // 16^8 > 2^31 tiles
@@ -89,6 +91,11 @@ struct TilePlan {
   int lanes_r;          // R: row lanes per pass (256 / chunk_w)
   int64_t tile_rows;    // multiple of R
   int64_t tiles;        // tiles per contract
+  // simulated tiles: the LAST rows of a contract are cut finer (tail_tile_rows = R, one pass per thread), so that the
+  // launch ends on small CTAs — the block scheduler hands tiles out in index order — instead of a ragged wave of big ones
+  int64_t main_tiles;   // tiles [0, main_tiles) have tile_rows rows and cover rows [0, main_rows)
+  int64_t main_rows;
+  int64_t tail_tile_rows;
   TreePlan tree;
 };
 
@@ -101,9 +108,10 @@ static int64_t env_int(const char* name, int64_t fallback) {
 // `streaming`: the tile's source is an HBM-resident matrix (payoffs / staged terminals), so tiles
 // are sized for bandwidth (>= 64 KiB of input each, a few thousand CTAs) instead of for
 // load-balancing a compute-bound simulation.  Simulated tiles (`timesteps` > 0) are sized for about
-// TARGET_TILES CTAs per launch but never below MIN_TILE_PATH_STEPS path-steps, so that short paths
-// (the reference's own tests run one timestep) do not drown in per-tile bookkeeping.
-// One tile = one CTA, handed out by the hardware block scheduler.  (A persistent grid drawing tiles
+// TARGET_TILES CTAs per launch (TARGET_TILES_FINE_TAIL main tiles + a fine tail when the launch holds one
+// contract) but never below MIN_TILE_PATH_STEPS path-steps, so that short paths (the reference's own tests
+// run one timestep) do not drown in per-tile bookkeeping.
+// One tile = one CTA, handed out by the hardware block scheduler in index order.  (A persistent grid drawing tiles
 // from a device counter was measured and rejected: the warp scheduler is not fair between resident
 // CTAs — in one 1.4 ms launch some CTAs completed 53 tiles and others 4 — so the last tiles of starved
 // CTAs stretched the tail by 100-400 us; freshly launched CTAs rotate through the priorities instead.
@@ -114,18 +122,33 @@ static TilePlan make_plan(int64_t n_contracts, int64_t rows_local, int64_t n, bo
   p.chunk_w = static_cast<int>(std::min<int64_t>(n, CF_BLOCK));
   p.lanes_r = CF_BLOCK / p.chunk_w;
   const int64_t R = p.lanes_r;
-  static const int64_t target_tiles = env_int("SMC_TARGET_TILES", TARGET_TILES);  // tuning knob
-  const int64_t target = streaming ? STREAM_TILES : target_tiles;
+  static const int64_t target_env = env_int("SMC_TARGET_TILES", 0);  // tuning knobs
+  static const int64_t tail_tiles = env_int("SMC_TAIL_TILES", TAIL_TILES + 1) - 1;  // SMC_TAIL_TILES=1 switches the fine tail off
+  // Fine tail (single-contract simulated launches): the last TAIL_TILES smallest-size tiles' worth of rows (at most a quarter of
+  // the rows) are cut into tiles of the smallest size, so the launch ends on small CTAs — the block scheduler hands tiles out in
+  // index order — and the MAIN tiles can be large (less per-CTA bookkeeping) without a ragged last wave of big ones:
+  // 1.300 -> 1.282 ms at config c2.  Shape-only, like everything else here.
+  const bool simulated = !streaming && timesteps > 0;
+  const int64_t smallest = !simulated ? R : std::max<int64_t>(R, ((MIN_TILE_PATH_STEPS + n * timesteps - 1) / (n * timesteps) + R - 1) / R * R);
+  const bool fine_tail = simulated && tail_tiles > 0 && n_contracts == 1 && rows_local / 4 >= smallest;
+  const int64_t target = streaming ? STREAM_TILES : (target_env > 0 ? target_env : (fine_tail ? TARGET_TILES_FINE_TAIL : TARGET_TILES));
   int64_t want = (n_contracts * rows_local + target - 1) / target;
   if (streaming) want = std::max<int64_t>(want, (16384 + n - 1) / n);  // >= 16 Ki elements per tile
-  if (!streaming && timesteps > 0) {
-    const int64_t per_row = n * timesteps;
-    want = std::max<int64_t>(want, (MIN_TILE_PATH_STEPS + per_row - 1) / per_row);
-  }
+  if (simulated) want = std::max<int64_t>(want, smallest);
   want = std::max<int64_t>(want, 1);
   p.tile_rows = (want + R - 1) / R * R;
   p.tile_rows = std::min<int64_t>(p.tile_rows, (rows_local + R - 1) / R * R);
-  p.tiles = (rows_local + p.tile_rows - 1) / p.tile_rows;
+  p.main_rows = rows_local;
+  p.tail_tile_rows = p.tile_rows;
+  if (fine_tail && p.tile_rows > smallest) {
+    const int64_t tail_rows = std::min<int64_t>(tail_tiles * smallest, rows_local / 4) / smallest * smallest;
+    if (tail_rows > 0) {
+      p.main_rows = rows_local - tail_rows;
+      p.tail_tile_rows = smallest;
+    }
+  }
+  p.main_tiles = (p.main_rows + p.tile_rows - 1) / p.tile_rows;
+  p.tiles = p.main_tiles + (rows_local - p.main_rows + p.tail_tile_rows - 1) / p.tail_tile_rows;
   p.tree = make_tree(p.tiles);
   return p;
 }
@@ -149,6 +172,7 @@ struct TileParams {
   int64_t row_begin, row_end;   // local batch rows
   int64_t paths_local;          // (row_end - row_begin) * n
   int64_t tile_rows, tiles;
+  int64_t main_tiles, main_rows, tail_tile_rows;  // fine tail (TilePlan)
   int chunk_w, lanes_r;
   int chunk_shift;              // log2(chunk_w) when it is a power of two, else -1
   int scheme;
@@ -848,8 +872,9 @@ __global__ void __launch_bounds__(CF_BLOCK, SRC != SRC_FUSED ? 0 : (sizeof(Real)
   if (c_local >= p.launch_contracts) return;
   const int64_t tile = blockIdx.x;
   const int64_t c_global = p.contract0 + c_local;
-  const int64_t row0 = p.row_begin + tile * p.tile_rows;
-  const int64_t row1 = min(row0 + p.tile_rows, p.row_end);
+  const bool in_tail = tile >= p.main_tiles;
+  const int64_t row0 = p.row_begin + (in_tail ? p.main_rows + (tile - p.main_tiles) * p.tail_tile_rows : tile * p.tile_rows);
+  const int64_t row1 = in_tail ? min(row0 + p.tail_tile_rows, p.row_end) : min(row0 + p.tile_rows, p.row_begin + p.main_rows);
   constexpr bool RAGGED = FORM != 0;
 
   SimConsts<Real> k{};
@@ -1191,6 +1216,9 @@ static TileParams base_params(const smc_fused_args* a, const TilePlan& plan) {
   p.paths_local = (a->batch_end - a->batch_begin) * a->network_size;
   p.tile_rows = plan.tile_rows;
   p.tiles = plan.tiles;
+  p.main_tiles = plan.main_tiles;
+  p.main_rows = plan.main_rows;
+  p.tail_tile_rows = plan.tail_tile_rows;
   p.chunk_w = plan.chunk_w;
   p.lanes_r = plan.lanes_r;
   p.tree = plan.tree;
@@ -1409,12 +1437,14 @@ extern "C" int smc_cf_fused_plan(const smc_fused_args* a, int64_t* out, int capa
   clear_error();
   if (int e = check_args("smc_cf_fused_plan", a)) return e;
   const TilePlan plan = sim_plan(a);
-  SMC_REQUIRE(out != nullptr && capacity >= 5, "smc_cf_fused_plan: out needs 5 entries");
+  SMC_REQUIRE(out != nullptr && capacity >= 7, "smc_cf_fused_plan: out needs 7 entries");
   out[0] = plan.tiles;
   out[1] = plan.tile_rows;
   out[2] = plan.lanes_r;
   out[3] = plan.tree.levels;
   out[4] = plan.tree.count[plan.tree.levels];
+  out[5] = plan.main_tiles;
+  out[6] = plan.tail_tile_rows;
   return SMC_OK;
 }
 #endif
@@ -1713,6 +1743,9 @@ extern "C" int smc_cf_fft_mean(const void* mat, int64_t batches, int64_t n, int 
   p.paths_local = batches * n;
   p.tile_rows = plan.tile_rows;
   p.tiles = plan.tiles;
+  p.main_tiles = plan.main_tiles;
+  p.main_rows = plan.main_rows;
+  p.tail_tile_rows = plan.tail_tile_rows;
   p.chunk_w = plan.chunk_w;
   p.lanes_r = plan.lanes_r;
   p.tree = plan.tree;

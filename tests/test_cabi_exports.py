@@ -128,8 +128,13 @@ def test_tile_plan_depends_on_the_problem_shape_only() -> None:
             rows = hi - lo
             assert plan["row_lanes"] == max(1, 256 // min(N, 256)), name
             assert plan["tile_rows"] % plan["row_lanes"] == 0 and plan["tile_rows"] >= 1, name
-            assert (plan["tiles"] - 1) * plan["tile_rows"] < rows <= plan["tiles"] * plan["tile_rows"], (name, plan, rows)
-            assert plan["tile_rows"] * N * T >= 16384 or plan["tiles"] == 1, (name, plan)
+            assert plan["tail_tile_rows"] % plan["row_lanes"] == 0 and 1 <= plan["tail_tile_rows"] <= plan["tile_rows"], name
+            # main tiles of tile_rows rows, then (single-contract launches) a fine tail of tail_tile_rows rows: together exactly `rows`
+            main, tail = plan["main_tiles"], plan["tiles"] - plan["main_tiles"]
+            covered_max = main * plan["tile_rows"] + tail * plan["tail_tile_rows"]
+            assert covered_max >= rows and covered_max - rows < plan["tile_rows"] + plan["tail_tile_rows"], (name, plan, rows)
+            assert tail == 0 or (C == 1 and tail * plan["tail_tile_rows"] <= rows // 4 + plan["tail_tile_rows"]), (name, plan)
+            assert plan["tail_tile_rows"] * N * T >= 16384 or plan["tiles"] == 1 or plan["tail_tile_rows"] == plan["row_lanes"], (name, plan)
             assert 1 <= plan["root_fan_in"] <= 16, (name, plan)
             width, level = plan["tiles"], 0
             while width > 16:
