@@ -8,4 +8,4 @@ for what in fused fused_f64 fused_c3; do
 done
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-workloads > gpurun_out/r2_launches_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-workloads > gpurun_out/r2_launches_ncu.log 2>&1
-tail -2 gpurun_out/r2_prof_ncu_fused.log gpurun_out/r2_launches_ncu.log
+tail -n 2 gpurun_out/r2_prof_ncu_fused.log; tail -n 2 gpurun_out/r2_launches_ncu.log
