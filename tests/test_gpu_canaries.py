@@ -126,7 +126,8 @@ def _group(rank, world, bufs, cap, n, epoch, timeout_ms=0):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
-@pytest.mark.parametrize("N,B,norm", [(64, 40, _cabi.SMC_RAW), (48, 21, _cabi.SMC_RAW), (16, 33, _cabi.SMC_NORMALIZE)])
+@pytest.mark.parametrize("N,B,norm", [(64, 40, _cabi.SMC_RAW), (48, 21, _cabi.SMC_RAW), (16, 33, _cabi.SMC_NORMALIZE),
+                                      (1024, 5, _cabi.SMC_RAW)])  # N = 1024: the transform leaves the step kernel (separate exchange-finalise kernel)
 def test_peer_exchange_stays_inside_its_buffers(dtype, N, B, norm) -> None:
     """The exchange layout (data slots, per-contract flags, small all-reduce region, status word) addressed by both
     ranks of a 2-rank group, each rank on its own stream of the same device: guard bands around BOTH exchange

@@ -149,6 +149,34 @@ def test_opt_in_stream_through_the_engine_api() -> None:
 
 
 @pytest.mark.parametrize("prec", ["float64", "float32"])
+@pytest.mark.parametrize("norm", [_cabi.SMC_RAW, _cabi.SMC_NORMALIZE])
+def test_fine_tail_tile_plan_covers_every_row_exactly_once(prec, norm) -> None:
+    """A single-contract launch of this size ends on a fine tail (main tiles of 14 rows, then tiles of 12 rows for the
+    last rows; smc_cf_fused_plan), its four batch shards do not: the shards' partial CFs must add up to the whole —
+    a row simulated twice or not at all would show at the 1e-5 level."""
+    dtype = torch.float64 if prec == "float64" else torch.float32
+    T, N, B = 12, 128, 40000
+    contracts = torch.tensor(np.asarray([ODD]), device="cuda")
+    whole_args = _cabi.make_fused_args(contracts, 1, T, N, B, dtype, _cabi.SMC_LOG_EULER, norm, 11, 2)
+    plan = _cabi.cf_fused_plan(whole_args)
+    assert plan["main_tiles"] < plan["tiles"] and plan["tail_tile_rows"] < plan["tile_rows"], plan
+    whole = _cabi.cf_fused(whole_args, contracts.device, dtype).cpu().numpy()
+    cuts = [0, 10000, 20001, 29999, 40000]
+    shards = [_cabi.make_fused_args(contracts, 1, T, N, B, dtype, _cabi.SMC_LOG_EULER, norm, 11, 2, batch_begin=lo, batch_end=hi)
+              for lo, hi in zip(cuts[:-1], cuts[1:])]
+    for a in shards:
+        p = _cabi.cf_fused_plan(a)
+        assert p["main_tiles"] == p["tiles"], p  # no fine tail in the shards
+    if norm == _cabi.SMC_RAW:
+        total = sum(_cabi.cf_fused(a, contracts.device, dtype).cpu().numpy() for a in shards)
+    else:
+        staged = [_cabi.fused_terminal(a, contracts.device, dtype) for a in shards]
+        tsum = sum(s for _, s in staged)
+        total = sum(_cabi.cf_from_terminal(a, t, tsum, dtype).cpu().numpy() for a, (t, _) in zip(shards, staged))
+    assert rel_max(total, whole) <= (1e-13 if prec == "float64" else 2e-6)
+
+
+@pytest.mark.parametrize("prec", ["float64", "float32"])
 def test_stepwise_exponential_variant_agrees(prec) -> None:
     """prod_j exp(x_j) == exp(sum_j x_j): the per-step-exp kernel and the log-sum kernel agree."""
     dtype = torch.float64 if prec == "float64" else torch.float32
