@@ -44,10 +44,8 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 /* adjacent columns sharing one block */
 static int short_group(int dtype, int64_t rows) { return (dtype == 0 && rows >= 1 && rows <= 3) ? (int)(6 / rows) : 1; }
 static double uniform_21(uint32_t field) { return ((double)field + 0.5) * 0x1p-21; }
-static double uniform_f64(uint32_t hi, uint32_t lo) {
-  const uint64_t m = ((uint64_t)(hi & 0xfffffu) << 32) | lo;
-  return ((double)m + 0.5) * 0x1p-52;
-}
+/* float64 stream: 43-bit radius field w0 << 11 | w1 >> 21, 21-bit angle field w1 & 0x1fffff of a pair's two words */
+static double uniform_43(uint32_t w0, uint32_t w1) { return ((double)(((uint64_t)w0 << 11) | (w1 >> 21)) + 0.5) * 0x1p-43; }
 static void box_muller(double u1, double u2, double* even, double* odd) {
   const double r = sqrt(-2.0 * log(u1)), theta = 2.0 * M_PI * (u2 - 0.5);
   *even = r * cos(theta);
@@ -55,7 +53,7 @@ static void box_muller(double u1, double u2, double* even, double* odd) {
 }
 
 /* one block of normals for column `col`, row group q: 6 values (float32 stream: 21-bit fields,
- * three pairs, rare refinement block) or 2 values (float64 stream).  See oracle/philox.py. */
+ * three pairs, rare refinement block) or 4 values (float64 stream: two pairs).  See oracle/philox.py. */
 static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, uint64_t k, double z[6]) {
   const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
   uint32_t ctr[4] = {col, q, (uint32_t)k, (uint32_t)(k >> 32) & 0x7fffffffu}, x[4];
@@ -77,7 +75,8 @@ static void normals_block(int dtype, uint32_t col, uint32_t q, uint64_t seed, ui
   } else {
     ctr[3] |= F64_STREAM_BIT;
     oracle_philox4x32_10(ctr, key, x);
-    box_muller(uniform_f64(x[0], x[1]), uniform_f64(x[2], x[3]), &z[0], &z[1]);
+    box_muller(uniform_43(x[0], x[1]), uniform_21(x[1] & 0x1fffffu), &z[0], &z[1]);
+    box_muller(uniform_43(x[2], x[3]), uniform_21(x[3] & 0x1fffffu), &z[2], &z[3]);
   }
 }
 
@@ -92,7 +91,7 @@ void oracle_normals(void* out, int64_t rows, int64_t cols, int dtype, uint64_t s
     }
     return;
   }
-  const int per = dtype == 0 ? 6 : 2;
+  const int per = dtype == 0 ? 6 : 4;
   const int64_t nq = (rows + per - 1) / per;
   for (int64_t j = 0; j < cols; ++j) {
     for (int64_t q = 0; q < nq; ++q) {
@@ -132,7 +131,7 @@ double oracle_terminal_range(const double* contract, int64_t T, int dtype, int l
   const double X0 = contract[0], Tm = contract[2], r = contract[3], d = contract[4], v = contract[5];
   const double dt = Tm / (double)T, sqrt_dt = sqrt(dt); /* gbm.py:411,243 */
   const double drift = log_flag ? r - d - 0.5 * v * v : r - d;
-  const int per = dtype == 0 ? 6 : 2;
+  const int per = dtype == 0 ? 6 : 4;
   const int G = short_group(dtype, T);
   double tsum = 0.0;
   for (int64_t j = path_begin; j < path_end; ++j) {

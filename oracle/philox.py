@@ -28,12 +28,18 @@ Stream definition
   layouts never share a block — and element (i, j) is normal number (j % G) * rows + i of that block
   (normals 2p, 2p+1 = even / odd value of pair p, as above; refinement counter word 0xC0000000).
   rows = 1: six columns per block; rows = 2: three; rows = 3: two.  rows = 4, 5 keep the general layout.
-* float64: one block per (column j, row-pair q = i // 2): counter as above with the
+* float64: one block per (column j, row-group q = i // 4): counter as above with the
   top bit of word 3 set (``0x80000000 | k >> 32``) so the two precisions never share a
-  block; (x0, x1) -> 52-bit radius uniform, (x2, x3) -> 52-bit angle uniform, one pair.
+  block; its 128 bits feed TWO Box–Muller pairs, 64 bits each — (x0, x1) -> rows 4q, 4q+1 and
+  (x2, x3) -> rows 4q+2, 4q+3 — with, for the words (w0, w1) of a pair,
+    radius field  R = w0 << 11 | w1 >> 21      (43 bits: the radius reaches 7.7 sigma, no refinement needed)
+    angle field   A = w1 & 0x1fffff            (21 bits, as in the float32 stream)
+  (since round 2; one pair per block with two 52-bit uniforms before: the integer work of a block bounded the
+  float64 kernels — profiles/r2_pipe_overlap_f64_microbench.txt — and 64 random bits per pair are what the
+  float32 stream's statistical battery already vouches for at 42).  All ARITHMETIC stays float64.
 * uniforms (exactly representable, open interval):
     f32: u = (F + 0.5) * 2**-21 for a 21-bit field F (radius: F = R_p unless R_p == 0, see above)
-    f64: m = ((hi & 0xfffff) << 32) | lo;  u = (m + 0.5) * 2**-52
+    f64: u1 = (R + 0.5) * 2**-43,  u2 = (A + 0.5) * 2**-21
 * Box–Muller: r = sqrt(-2 ln u1), theta = 2 pi (u2 - 0.5); even row = r cos(theta),
   odd row = r sin(theta).
 
@@ -122,9 +128,14 @@ def uniform_refined(y: np.ndarray) -> np.ndarray:
     return ((y.astype(np.uint64) >> np.uint64(9)).astype(np.float64) + 0.5) * 2.0**-44
 
 
-def uniform_f64(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
-    m = ((hi.astype(np.uint64) & np.uint64(0xFFFFF)) << np.uint64(32)) | lo.astype(np.uint64)
-    return (m.astype(np.float64) + 0.5) * 2.0**-52
+def f64_fields(w0: np.ndarray, w1: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    """43-bit radius and 21-bit angle fields of one float64 pair (two words of a block)."""
+    w0, w1 = w0.astype(np.uint64), w1.astype(np.uint64)
+    return (w0 << np.uint64(11)) | (w1 >> np.uint64(21)), w1 & np.uint64(0x1FFFFF)
+
+
+def uniform_43(field: np.ndarray) -> np.ndarray:
+    return (field.astype(np.float64) + 0.5) * 2.0**-43  # exact: 44 significant bits
 
 
 def _box_muller(u1: np.ndarray, u2: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -195,12 +206,17 @@ def normals_matrix(
             z, rad = z[:rows], rad[:rows]
         z = z.astype(np.float32)
     elif dtype == np.float64:
-        nq = (rows + 1) // 2
+        nq = (rows + 3) // 4
         q = np.arange(nq, dtype=np.uint32)[:, None]
         x0, x1, x2, x3 = philox4x32_10((j, q, k_lo, F64_STREAM_BIT | k_hi), key, rounds)
-        za, zb, ra = _box_muller(uniform_f64(x0, x1), uniform_f64(x2, x3))
-        z = np.stack([za, zb], axis=1).reshape(2 * nq, -1)[:rows]
-        rad = np.stack([ra, ra], axis=1).reshape(2 * nq, -1)[:rows]
+        zs, rs = [], []
+        for w0, w1 in ((x0, x1), (x2, x3)):  # two pairs per block: rows 4q, 4q+1 and 4q+2, 4q+3
+            radius, angle = f64_fields(w0, w1)
+            ze, zo, r = _box_muller(uniform_43(radius), uniform_21(angle))
+            zs += [ze, zo]
+            rs += [r, r]
+        z = np.stack(zs, axis=1).reshape(4 * nq, -1)[:rows]
+        rad = np.stack(rs, axis=1).reshape(4 * nq, -1)[:rows]
     else:
         raise ValueError(f"unsupported dtype {dtype}")
     z = np.ascontiguousarray(z)

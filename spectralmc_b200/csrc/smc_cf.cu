@@ -433,7 +433,7 @@ template <int SCHEME, bool RAGGED>
 __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, uint32_t col, int64_t timesteps,
                                                     const PhiloxKeys& keys, uint32_t k_lo, uint32_t k_hi) {
   double acc = SCHEME == SMC_LOG_EULER ? 0.0 : k.X0;
-  const uint32_t nq = static_cast<uint32_t>(timesteps >> 1);
+  const uint32_t nq = static_cast<uint32_t>(timesteps >> 2);  // whole blocks: four normals (two pairs) each
 #ifndef SMC_F64_UNROLL
 #define SMC_F64_UNROLL 1
 #endif
@@ -441,18 +441,21 @@ __device__ __forceinline__ double simulate_terminal(const SimConsts<double>& k, 
 #pragma unroll kUnroll
   for (uint32_t q = 0; q < nq; ++q) {
     if (SCHEME == SMC_LOG_EULER) {
-      acc = normals2_sum_f64(col, q, k_lo, k_hi, keys, acc);
+      acc = normals4_sum_f64(col, q, k_lo, k_hi, keys, acc);
     } else {
-      double z[2];
-      normals2_f64(col, q, k_lo, k_hi, keys, z);
-      consume<double, SCHEME>(acc, z[0], k);
-      consume<double, SCHEME>(acc, z[1], k);
+      double z[4];
+      normals4_f64(col, q, k_lo, k_hi, keys, z);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) consume<double, SCHEME>(acc, z[u], k);
     }
   }
-  if (timesteps & 1) {
-    double z[2];
-    normals2_f64(col, nq, k_lo, k_hi, keys, z);
-    consume<double, SCHEME>(acc, z[0], k);
+  const int rem = static_cast<int>(timesteps & 3);
+  if (rem) {
+    double z[4];
+    normals4_f64(col, nq, k_lo, k_hi, keys, z, rem > 2 ? 2 : 1);
+#pragma unroll
+    for (int u = 0; u < 3; ++u)
+      if (u < rem) consume<double, SCHEME>(acc, z[u], k);
   }
   if (SCHEME == SMC_LOG_EULER) return k.X0 * exp(fma(k.lin1, acc, k.lin0));
   return acc;

@@ -260,70 +260,46 @@ __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t 
   normals6_f32_impl<true>(col, q, k_lo, k_hi, key, z, unused);
 }
 
-// ---- float64 block: 4 words -> 1 pair --------------------------------------------------
-// log / sincospi specialised to the arguments Box–Muller produces (u in (0,1), a normal number;
-// |angle / pi| <= 1), with the polynomial coefficients in __constant__ memory so each DFMA takes
-// its coefficient as a constant-bank operand.  libdevice's general-purpose versions made ptxas
-// rebuild ~40 64-bit literals per iteration (80 of 240 issue slots of the float64 loop).  The
-// polynomials are the classical minimax sets of Sun's FDLIBM (k_sin.c, k_cos.c, e_log.c; error
-// < 1 ulp); tests/test_gpu_normals.py holds the device output to 1e-13 of the float64 oracle.
+// ---- float64 block: 4 words -> 2 pairs (oracle/philox.py) -------------------------------
+// One Philox block feeds TWO Box-Muller pairs, 64 bits each.  The words (w0, w1) of a pair:
+//   radius field R = w0 << 11 | w1 >> 21 (43 bits), angle field A = w1 & 0x1fffff (21 bits).
+// Both uniforms are put together as the mantissa of a double in [1, 2), so no integer -> float conversion runs:
+//   1 + (R + 0.5) 2^-43 : high word 0x3ff00000 | R >> 23, low word (R << 9 | 0x100) mod 2^32
+//   1 + (A + 0.5) 2^-21 : high word 0x3ff00000 | A >> 1,  low word (A & 1) << 31 | 0x40000000
+//
+// Logarithm, square root and sine / cosine are specialised to the arguments Box-Muller produces (u in (0, 1), a normal
+// number; -2 ln u in (0, 62); |angle / pi| <= 1) and written for the FP64 pipe, which bounds these kernels (DFMA issues
+// every 2 cycles per warp, profiles/r2_pipe_overlap_f64_microbench.txt): every FP64 instruction that is not needed for
+// 1e-13 is gone, and the polynomial coefficients live in __constant__ memory so each DFMA takes its coefficient as a
+// constant-bank operand (libdevice's general-purpose versions made ptxas rebuild ~40 64-bit literals per iteration and
+// carry a range test, a branch and an out-of-line slow path per division / square root).  The polynomials are the
+// classical minimax sets of Sun's FDLIBM (k_sin.c, k_cos.c, e_log.c); tests/test_gpu_normals.py holds the device
+// output to 1e-13 of the float64 oracle.  43 FP64 arithmetic instructions per pair (59 with libdevice-style last-bit
+// corrections, 51 before the radius was computed as one chain):
+//   radius (24)  x = -2 ln u = -2 k ln 2 + s2 (2 + R(s2^2)),  s2 = -2 f / (2 + f) = f / -(1 + f / 2),  u = 2^k (1 + f):
+//                the quotient is MUFU.RCP64H (2^-22) + one cubic Newton step (2^-66) without residual correction, the
+//                factor -2 rides on the divisor, FDLIBM's Lg_n are pre-divided by 4^n (exact) because s2^2 = 4 s^2, and
+//                2 + R is one Estrin pair.  r = sqrt(x) = g0 (1 + e / 2 + 3 e^2 / 8), g0 = x y0, e = 1 - g0 y0 from
+//                MUFU.RSQ64H (2^-22; truncation 5 e^3 / 16 < 2^-67), again without residual correction.
+//   angle (17)   v = 2 angle / pi = 4 (1 + u2) - 6 exactly; n = rint(v), x = (v - n) pi / 2 (one-word pi / 2: absolute
+//                error 2^-55), sin x = x + x z S(z), cos x = 1 + z (-1/2 + z C(z)), quadrant n mod 4.
 static __constant__ double kSinCoef[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
                                           -1.98412698298579493134e-04, 2.75573137070700676789e-06,
                                           -2.50507602534068634195e-08, 1.58969099521155010221e-10};
 static __constant__ double kCosCoef[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03,
                                           2.48015872894767294178e-05,  -2.75573143513906633035e-07,
                                           2.08757232129817482790e-09,  -1.13596475577881948265e-11};
-static __constant__ double kLogCoef[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
-                                          2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
-                                          1.479819860511658591e-01};
-static __constant__ double kLn2 = 6.93147180559945286227e-01;
-static __constant__ double kLogMisc[4] = {6.93147180369123816490e-01 /* ln2 hi */, 1.90821492927058770002e-10 /* ln2 lo */,
-                                          3.14159265358979311600e+00 /* pi hi */, 1.22464679914735317723e-16 /* pi lo */};
+// Lg_n / 4^n, n = 1..7 (e_log.c's Lg1..Lg7; the power-of-two scaling is exact)
+static __constant__ double kLogCoef[7] = {6.666666666666735130e-01 / 4.0,     3.999999999940941908e-01 / 16.0,
+                                          2.857142874366239149e-01 / 64.0,    2.222219843214978396e-01 / 256.0,
+                                          1.818357216161805012e-01 / 1024.0,  1.531383769920937332e-01 / 4096.0,
+                                          1.479819860511658591e-01 / 16384.0};
+static __constant__ double kF64Misc[5] = {-2.0 * 6.93147180559945286227e-01 /* -2 ln 2 */, 1.57079632679489655800e+00 /* pi / 2 */,
+                                          4.0, -6.0 /* v = 4 (1 + u2) - 6 */, 0.375};
 
-// Division and square root for the well-scaled positive arguments Box–Muller produces (no zero,
-// subnormal, infinite or NaN input can occur), from the MUFU seeds (RCP64H / RSQ64H, relative error
-// 2^-22) and FP64 Newton steps.  The compiler's general-purpose sequences carry a range test, a branch
-// and an out-of-line slow path per call (12 of the 113 non-FP64 issue slots of the float64 loop);
-// the results here are within 1 ulp (tests/test_gpu_normals.py holds the stream to 1e-13).
-#ifndef SMC_F64_LEAN
-#define SMC_F64_LEAN 1  // 1: the float64 Box-Muller without the last-bit corrections below (50 instead of 59 FP64 instructions per pair)
-#endif
-// SMC_F64_LEAN drops four refinements whose effect is below 2 ulp of the result — far inside the 1e-13
-// the float64 stream is held to (tests/test_gpu_normals.py) and the 1e-12 of the CF parity:
-//   the residual correction of the quotient (q = a r with r good to 2^-66 is within 1 ulp),
-//   the residual correction of the square root (g = x y, y good to 2^-66),
-//   the split (hi, lo) accumulation of k ln 2 in the logarithm (one FMA: |k| <= 52, error < 1 ulp of the result),
-//   the second word of pi in the angle (|r| <= 1/4: absolute error 2^-55).
-__device__ __forceinline__ double div_pos_f64(double a, double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  e = fma(e, e, e);                       // e + e^2
-  r = fma(r, e, r);                       // r (1 + e + e^2): relative error 2^-66
-  const double q = a * r;
-#if SMC_F64_LEAN
-  return q;
-#else
-  return fma(fma(-d, q, a), r, q);        // one residual correction
-#endif
-}
-__device__ __forceinline__ double sqrt_pos_f64(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(-x * y, y, 1.0);            // 1 - x y^2
-  y = fma(y * e, fma(e, 0.375, 0.5), y);           // y (1 + e/2 + 3 e^2 / 8)
-  const double g = x * y;
-#if SMC_F64_LEAN
-  return g;
-#else
-  return fma(fma(-g, g, x), 0.5 * y, g);           // g + (x - g^2) / (2 g)
-#endif
-}
-
-static __constant__ double kLogMisc2[2] = {2.0, 0x1p-52};  // angle / pi = 2 w + 2^-52 with constant-bank operands
-
-// natural log of u in (0, 1), u normal
-__device__ __forceinline__ double log_unit_interval(double u) {
+// r = sqrt(-2 ln u) for u = d - 1, d in [1, 2) with a non-zero mantissa (so u is a normal number in (0, 1))
+__device__ __forceinline__ double radius_f64(double d) {
+  const double u = d - 1.0;  // exact, and normalises the mantissa
   int hi = __double2hiint(u);
   const int lo = __double2loint(u);
   int k = (hi >> 20) - 1023;
@@ -333,97 +309,84 @@ __device__ __forceinline__ double log_unit_interval(double u) {
     k += 1;
   }
   const double f = __hiloint2double(hi, lo) - 1.0;
-  const double s = div_pos_f64(f, 2.0 + f);
-  const double z = s * s, w = z * z;
-  const double t1 = w * fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]);
-  const double t2 = z * fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
-  const double R = t1 + t2, hfsq = 0.5 * f * f, dk = static_cast<double>(k);
-#if SMC_F64_LEAN
-  return fma(dk, kLn2, f - fma(-s, hfsq + R, hfsq));  // k ln 2 + (f - (hfsq - s (hfsq + R)))
-#else
-  return dk * kLogMisc[0] - ((hfsq - fma(s, hfsq + R, dk * kLogMisc[1])) - f);
-#endif
+  const double dn = fma(f, -0.5, -1.0);  // -(2 + f) / 2
+  double rc;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc) : "d"(dn));
+  double e = fma(-dn, rc, 1.0);
+  e = fma(e, e, e);                      // e + e^2
+  rc = fma(rc, e, rc);                   // rc (1 + e + e^2): relative error 2^-66
+  const double s2 = f * rc;              // -2 s
+  const double z = s2 * s2, w = z * z;
+  const double even = fma(w, fma(w, fma(w, kLogCoef[5], kLogCoef[3]), kLogCoef[1]), 2.0);   // 2 + Lg2 z^2 + Lg4 z^4 + Lg6 z^6
+  const double odd = fma(w, fma(w, fma(w, kLogCoef[6], kLogCoef[4]), kLogCoef[2]), kLogCoef[0]);
+  const double x = fma(static_cast<double>(k), kF64Misc[0], s2 * fma(z, odd, even));  // -2 ln u > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double g = x * y;
+  const double e2 = fma(-g, y, 1.0);                       // 1 - x y^2
+  return fma(g * e2, fma(e2, kF64Misc[4], 0.5), g);       // g (1 + e / 2 + 3 e^2 / 8)
 }
 
-// sin(pi t), cos(pi t) for |t| <= 1
-__device__ __forceinline__ void sincospi_unit(double t, double& sn, double& cs) {
-  const double n = rint(2.0 * t);             // quadrant, in {-2 .. 2}
-  const double r = fma(n, -0.5, t);           // exact, |r| <= 1/4
-#if SMC_F64_LEAN
-  const double x = r * kLogMisc[2];                        // pi r
-#else
-  const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);  // pi r, two-term pi
-#endif
+// (s0, c0) = (sin, cos)(pi t - n pi / 2), n = rint(2 t), for t = 2 d - 3, d = 1 + u2 in [1, 2); returns n
+__device__ __forceinline__ int sincos_reduced_f64(double d, double& s0, double& c0) {
+  const double v = fma(d, kF64Misc[2], kF64Misc[3]);  // 2 t in [-2, 2), exact
+  const double n = rint(v);
+  const double x = (v - n) * kF64Misc[1];             // |x| <= pi / 4
   const double z = x * x;
   const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
   const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);
-  const double s0 = fma(x * z, ps, x);                 // sin x
-  const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));  // cos x
-  const int q = static_cast<int>(n) & 3;
-  const double a = (q & 1) ? c0 : s0, b = (q & 1) ? s0 : c0;
-  sn = (q & 2) ? -a : a;                       // q: 0 -> s, 1 -> c, 2 -> -s, 3 -> -c
-  cs = ((q + 1) & 2) ? -b : b;                 // q: 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
+  s0 = fma(x * z, ps, x);
+  c0 = fma(z, fma(z, pc, -0.5), 1.0);
+  return static_cast<int>(n);
 }
 
-// sin(pi t) + cos(pi t) with the quadrant signs folded in by XOR on the high words (no selects):
-// with n = rint(2 t), q = n mod 4 and (s0, c0) = (sin, cos)(pi (t - n/2)):
-//   cos(pi t) + sin(pi t) = sigma_c c0 + sigma_s s0,  sigma_c = -1 iff q in {2,3},  sigma_s = -1 iff q in {1,2}
-// (the two terms swap roles for odd q, which a SUM does not see).  Returned separately so the caller
-// can keep two FMAs into its accumulator: acc += r * c_term; acc += r * s_term.
-__device__ __forceinline__ void sincospi_unit_terms(double t, double& c_term, double& s_term) {
-  const double n = rint(2.0 * t);
-  const double r = fma(n, -0.5, t);
-#if SMC_F64_LEAN
-  const double x = r * kLogMisc[2];
-#else
-  const double x = fma(r, kLogMisc[3], r * kLogMisc[2]);
-#endif
-  const double z = x * x;
-  const double ps = fma(z, fma(z, fma(z, fma(z, fma(z, kSinCoef[5], kSinCoef[4]), kSinCoef[3]), kSinCoef[2]), kSinCoef[1]), kSinCoef[0]);
-  const double pc = fma(z, fma(z, fma(z, fma(z, fma(z, kCosCoef[5], kCosCoef[4]), kCosCoef[3]), kCosCoef[2]), kCosCoef[1]), kCosCoef[0]);
-  const double s0 = fma(x * z, ps, x);
-  const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
-  const uint32_t q = static_cast<uint32_t>(static_cast<int>(n));
-  const uint32_t flip_c = (q << 30) & 0x80000000u;               // bit 1 of q
-  const uint32_t flip_s = ((q ^ (q >> 1)) << 31);                // bit 0 of q xor bit 1 of q
-  c_term = __hiloint2double(__double2hiint(c0) ^ static_cast<int>(flip_c), __double2loint(c0));
-  s_term = __hiloint2double(__double2hiint(s0) ^ static_cast<int>(flip_s), __double2loint(s0));
+__device__ __forceinline__ double f64_radius(uint32_t w0, uint32_t w1) {
+  const uint32_t lo = (__funnelshift_l(w1, w0, 20) & 0xfffffe00u) | 0x100u;
+  return radius_f64(__hiloint2double(static_cast<int>((w0 >> 12) | 0x3ff00000u), static_cast<int>(lo)));
+}
+__device__ __forceinline__ double f64_angle(uint32_t w1) {  // 1 + u2
+  return __hiloint2double(static_cast<int>(((w1 >> 1) & 0x000fffffu) | 0x3ff00000u), static_cast<int>((w1 << 31) | 0x40000000u));
 }
 
-// acc + z[0] + z[1] of normals2_f64 (same draws; for the log-Euler sum, where the order of the two
-// normals of a pair does not matter)
-__device__ __forceinline__ double normals2_sum_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+// acc + the four normals of normals4_f64 (same draws; for the log-Euler sum, where the order of the normals of a block
+// does not matter).  cos(pi t) + sin(pi t) = sigma_c c0 + sigma_s s0 with sigma_c = -1 iff q in {2, 3}, sigma_s = -1 iff
+// q in {1, 2}, q = n mod 4 (the two terms swap roles for odd q, which a SUM does not see): the signs are XORed into the
+// high words, no selects.
+__device__ __forceinline__ double normals4_sum_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                                    const PhiloxKeys& key, double acc) {
   uint32_t x[4];
   philox4x32_10(col, q, k_lo, k_hi | F64_STREAM_BIT, key, x);
-  const double u1 =
-      __hiloint2double(static_cast<int>((x[0] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[1])) -
-      0x1.fffffffffffffp-1;
-  const double w =
-      __hiloint2double(static_cast<int>((x[2] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[3])) - 1.5;
-  const double r = sqrt_pos_f64(-2.0 * log_unit_interval(u1));
-  double ct, st;
-  sincospi_unit_terms(fma(w, kLogMisc2[0], kLogMisc2[1]), ct, st);
-  acc = fma(r, ct, acc);
-  return fma(r, st, acc);
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const double r = f64_radius(x[2 * p], x[2 * p + 1]);
+    double s0, c0;
+    const uint32_t n = static_cast<uint32_t>(sincos_reduced_f64(f64_angle(x[2 * p + 1]), s0, c0));
+    const uint32_t flip_c = (n << 30) & 0x80000000u;  // bit 1 of n
+    const uint32_t flip_s = (n ^ (n >> 1)) << 31;     // bit 0 xor bit 1
+    acc = fma(r, __hiloint2double(__double2hiint(c0) ^ static_cast<int>(flip_c), __double2loint(c0)), acc);
+    acc = fma(r, __hiloint2double(__double2hiint(s0) ^ static_cast<int>(flip_s), __double2loint(s0)), acc);
+  }
+  return acc;
 }
 
-__device__ __forceinline__ void normals2_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
-                                             const PhiloxKeys& key, double (&z)[2]) {
+// z[0..3] = rows 4q .. 4q + 3 of column `col`; `pairs` (1 or 2) = how many of the two pairs the caller needs
+__device__ __forceinline__ void normals4_f64(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
+                                             const PhiloxKeys& key, double (&z)[4], int pairs = 2) {
   uint32_t x[4];
   philox4x32_10(col, q, k_lo, k_hi | F64_STREAM_BIT, key, x);
-  // u = (m + 0.5) 2^-52, m = low 52 bits of (hi:lo); exact
-  const double u1 =
-      __hiloint2double(static_cast<int>((x[0] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[1])) -
-      0x1.fffffffffffffp-1;
-  const double w =
-      __hiloint2double(static_cast<int>((x[2] & 0x000fffffu) | 0x3ff00000u), static_cast<int>(x[3])) -
-      1.5;  // u2 - 0.5 - 2^-53
-  const double r = sqrt_pos_f64(-2.0 * log_unit_interval(u1));
-  double s, c;
-  sincospi_unit(fma(w, kLogMisc2[0], kLogMisc2[1]), s, c);  // angle / pi = 2 (u2 - 0.5), exact
-  z[0] = r * c;
-  z[1] = r * s;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    if (p < pairs) {
+      const double r = f64_radius(x[2 * p], x[2 * p + 1]);
+      double s0, c0;
+      const int n = sincos_reduced_f64(f64_angle(x[2 * p + 1]), s0, c0) & 3;
+      const double a = (n & 1) ? c0 : s0, b = (n & 1) ? s0 : c0;
+      z[2 * p] = r * (((n + 1) & 2) ? -b : b);  // cos: n = 0 -> c, 1 -> -s, 2 -> -c, 3 -> s
+      z[2 * p + 1] = r * ((n & 2) ? -a : a);    // sin: n = 0 -> s, 1 -> c, 2 -> -s, 3 -> -c
+    } else {
+      z[2 * p] = z[2 * p + 1] = 0.0;
+    }
+  }
 }
 
 // ---- per-contract constants --------------------------------------------------------------

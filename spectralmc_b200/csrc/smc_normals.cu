@@ -16,7 +16,7 @@ namespace SMC_NS {
 using namespace ::smc;  // shared helpers (smc_internal.h)
 
 constexpr int NORMALS_BLOCK = 256;
-constexpr int GROUPS_PER_THREAD = 4;  // row groups walked by one thread (24 rows f32 / 8 rows f64)
+constexpr int GROUPS_PER_THREAD = 4;  // row groups walked by one thread (24 rows f32 / 16 rows f64)
 
 template <int VEC>
 struct StoreVec;
@@ -105,22 +105,23 @@ __global__ void __launch_bounds__(NORMALS_BLOCK)
                               uint32_t k_lo, uint32_t k_hi) {
   const int64_t col0 = (static_cast<int64_t>(blockIdx.x) * NORMALS_BLOCK + threadIdx.x) * VEC;
   if (col0 >= cols) return;
-  const int64_t nq = (rows + 1) >> 1;
+  const int64_t nq = (rows + 3) >> 2;  // one block = four rows (two pairs) of a column
   for (int64_t q0 = static_cast<int64_t>(blockIdx.y) * GROUPS_PER_THREAD; q0 < nq;
        q0 += static_cast<int64_t>(gridDim.y) * GROUPS_PER_THREAD) {
 #pragma unroll
     for (int g = 0; g < GROUPS_PER_THREAD; ++g) {
       const int64_t q = q0 + g;
       if (q >= nq) break;
-      double z[VEC][2];
+      double z[VEC][4];
+      const int pairs = 4 * q + 2 < rows ? 2 : 1;
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         if (VEC == 1 || col0 + v < cols)
-          normals2_f64(static_cast<uint32_t>(col0 + v), static_cast<uint32_t>(q), k_lo, k_hi, key, z[v]);
+          normals4_f64(static_cast<uint32_t>(col0 + v), static_cast<uint32_t>(q), k_lo, k_hi, key, z[v], pairs);
       }
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int64_t row = 2 * q + rr;
+      for (int rr = 0; rr < 4; ++rr) {
+        const int64_t row = 4 * q + rr;
         if (row < rows) {
           double* dst = out + row * cols + col0;
           if (VEC == 2) {
@@ -174,7 +175,7 @@ static int launch_normals(void* out, int64_t rows, int64_t cols, int dtype, uint
   } else {
     const bool vec = allow_vec && aligned16 && (cols % 2 == 0);
     const int v = vec ? 2 : 1;
-    const int64_t nq = (rows + 1) / 2;
+    const int64_t nq = (rows + 3) / 4;
     dim3 grid(static_cast<unsigned>((cols / v + (cols % v != 0) + NORMALS_BLOCK - 1) / NORMALS_BLOCK),
               static_cast<unsigned>(std::min<int64_t>((nq + GROUPS_PER_THREAD - 1) / GROUPS_PER_THREAD, 65535)));
     if (vec)

@@ -78,7 +78,7 @@ def test_roofline_constants_match_the_built_kernels() -> None:
     assert sum(f32.values()) == bench.F32_LOOP["instructions"], dict(f32)
     assert sum(v for k, v in f32.items() if k.startswith("MUFU")) == bench.F32_LOOP["mufu"]
     assert f32["IMAD.WIDE.U32"] == 32 and not any(k.startswith(("DFMA", "DMUL", "DADD")) for k in f32)
-    f64 = _inner_loops(bench.F64_LOOP["kernel"])[0]  # one pair of float64 normals per iteration
+    f64 = _inner_loops(bench.F64_LOOP["kernel"])[0]  # one block = two pairs = four float64 normals per iteration
     assert sum(f64.values()) == bench.F64_LOOP["instructions"], dict(f64)
     assert sum(v for k, v in f64.items() if k.startswith(("DFMA", "DMUL", "DADD"))) == bench.F64_LOOP["fp64"]
 

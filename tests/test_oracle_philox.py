@@ -67,9 +67,20 @@ def test_uniforms_are_exact_and_open() -> None:
     y = np.array([0, 2**32 - 1], dtype=np.uint32)
     r = philox.uniform_refined(y)
     assert r[0] == 2.0**-45 and 0 < r[1] < 2.0**-21 and np.all(r.astype(np.float32).astype(np.float64) == r)
-    hi = np.array([0, 0xFFFFFFFF], dtype=np.uint32)
-    d = philox.uniform_f64(hi, hi)
-    assert 0 < d[0] < d[1] < 1 and d[0] == 2.0**-53
+    w = np.array([0, 0xFFFFFFFF], dtype=np.uint32)
+    radius, angle = philox.f64_fields(w, w)
+    assert [int(v) for v in radius] == [0, 2**43 - 1] and [int(v) for v in angle] == [0, 2**21 - 1]
+    d = philox.uniform_43(radius)
+    assert 0 < d[0] < d[1] < 1 and d[0] == 2.0**-44 and d[1] == 1 - 2.0**-44
+
+
+def test_float64_fields_partition_the_pair() -> None:
+    """The 43-bit radius field and the 21-bit angle field of a float64 pair use each of its 64 bits exactly once."""
+    for bit in range(64):
+        w0 = np.array([(1 << bit) if bit < 32 else 0], dtype=np.uint32)
+        w1 = np.array([(1 << (bit - 32)) if bit >= 32 else 0], dtype=np.uint32)
+        radius, angle = philox.f64_fields(w0, w1)
+        assert int(radius[0] != 0) + int(angle[0] != 0) == 1, bit
 
 
 def test_float32_fields_partition_the_block() -> None:
