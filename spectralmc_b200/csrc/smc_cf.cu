@@ -342,7 +342,7 @@ __device__ __forceinline__ float simulate_path_f32(const SimConsts<float>& k, ui
     constexpr int kUnrollX2 = SMC_F32X2_UNROLL;
 #pragma unroll kUnrollX2
     for (; q + 1 < nq; q += 2) acc2 = normals12_sum_f32x2(col, q, k_lo, k_hi, keys, acc2, min_word);
-    acc = acc2.x + acc2.y;
+    acc = (acc2.x + acc2.y) * 1.41421356237309505f;  // normals12_sum_f32x2 accumulates (z_even + z_odd) / sqrt(2)
   }
 #pragma unroll kUnroll
   for (; q < nq; ++q) {

@@ -221,20 +221,24 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   return unpack_f32x2(d);
 }
 
-// Two Box–Muller pairs at once, accumulated: acc += (z_even, z_odd) of pair A in lane x and of
-// pair B in lane y.  Same values per lane as box_muller_f32 (identical operations, packed).
+// Two Box–Muller pairs at once, accumulated: acc += (z_even + z_odd) / sqrt(2) of pair A in lane x and of pair B in
+// lane y.  Only the SUM of a pair's two normals enters the log-Euler path, and
+//   r cos(theta) + r sin(theta) = sqrt(2) r sin(theta + pi / 4),
+// so ONE MUFU.SIN replaces MUFU.COS + MUFU.SIN — three MUFUs per pair instead of four on the XU pipe that bounds the
+// kernel — and the pi / 4 rides in the constant of the FFMA that forms the angle.  The caller multiplies the path's
+// accumulated sum by sqrt(2) once.  (Same draws as box_muller_f32; the MUFU error per pair is that of one sine.)
 __device__ __forceinline__ float2 box_muller_sum_f32x2(float2 radius_unit, float2 angle_unit, float2 acc) {
   const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffff8p-1f, -0x1.fffff8p-1f));
+  // theta + pi / 4 = 2 pi angle_unit - (3 pi - 2 pi 2^-22) + pi / 4
   const float2 theta = fma_f32x2(angle_unit, make_float2(6.28318530717958648f, 6.28318530717958648f),
-                                 make_float2(-9.424776462741265f, -9.424776462741265f));
+                                 make_float2(-8.639378299343817f, -8.639378299343817f));
   const float2 m = mul_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)),
                              make_float2(-1.38629436111989062f, -1.38629436111989062f));
   const float2 r = make_float2(mufu_sqrt(m.x), mufu_sqrt(m.y));
-  acc = fma_f32x2(r, make_float2(mufu_cos(theta.x), mufu_cos(theta.y)), acc);
   return fma_f32x2(r, make_float2(mufu_sin(theta.x), mufu_sin(theta.y)), acc);
 }
 
-// Sum of the 12 normals of row groups q and q + 1 (coarse radius uniforms, like REFINE = false),
+// Sum of the 12 normals of row groups q and q + 1 (coarse radius uniforms, like REFINE = false), divided by sqrt(2),
 // added to acc.x + acc.y.  Three packed Box–Muller evaluations over the six pairs.
 __device__ __forceinline__ float2 normals12_sum_f32x2(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
                                                       const PhiloxKeys& key, float2 acc, uint32_t& min_word) {
