@@ -10,6 +10,7 @@ CuPy XORWOW bits are third-party and unpinned), so trust has to 
 * serial correlation along a path at lags 1..6 (within and across the 6-row blocks) and across adjacent columns;
 * a pricing check where the tail matters: deep out-of-the-money / in-the-money puts at 2^31 paths, float32 stream
   vs float64 stream vs Black-76, within 4 standard errors.
+* the float64 stream (two pairs per block, 43-bit radius + 21-bit angle field per pair) audited from its output at 1.3e8 normals.
 Budget: well under a minute on a B200.
 """
 
@@ -157,3 +158,40 @@ def test_deep_out_of_the_money_prices(strike_ratio, stream_version) -> None:
         # float32 path arithmetic adds a relative ~1e-7 bias to every payoff: far below one standard error here
         assert abs(prices[dtype] - analytic) < 4.0 * se + 2e-7 * analytic, (dtype, prices[dtype], analytic, se)
     assert abs(prices[torch.float32] - prices[torch.float64]) < 6.0 * se + 2e-7 * analytic
+
+
+@pytest.mark.parametrize("stream_version", [0, 1])
+def test_float64_stream_at_scale(stream_version) -> None:
+    """The float64 stream (two pairs per block: 43-bit radius and 21-bit angle field per pair) audited from its OUTPUT,
+    1.3e8 normals: each pair is taken apart again — u1 = exp(-r^2 / 2) and u2 = atan2(z_odd, z_even) / 2 pi + 1/2 must
+    be uniform (chi-square over 4096 cells each) and independent of each other — plus moments, tail counts against the
+    normal law and correlations along a path (within a pair, across the two pairs of a block, across blocks)."""
+    rows, cols = 64, 1 << 21
+    z = torch.empty((rows, cols), dtype=torch.float64, device=DEV)
+    _cabi.philox_normals(z, 20260318, 9, stream_version=stream_version)
+    n = z.numel()
+    for p, (mean, var) in enumerate([(0.0, 1.0), (1.0, 2.0), (0.0, 15.0), (3.0, 96.0)], start=1):
+        m = float((z**p).mean())
+        assert abs(m - mean) < 5 * math.sqrt(var / n), (p, m)
+    a = z.abs()
+    for t in (3.0, 4.0, 5.0):
+        expect = n * 2.0 * stats.norm.sf(t)
+        got = int((a > t).sum())
+        assert abs(got - expect) < 5 * math.sqrt(expect) + 1, (t, got, expect)
+    even, odd = z[0::2], z[1::2]  # rows 2p, 2p + 1 of a column are one Box-Muller pair
+    u1 = torch.exp(-0.5 * (even * even + odd * odd))
+    u2 = torch.atan2(odd, even) / (2 * math.pi) + 0.5
+    cells = 4096
+    pairs = u1.numel()
+    for name, u in (("radius", u1), ("angle", u2)):
+        counts = torch.bincount((u * cells).long().clamp_(0, cells - 1).ravel(), minlength=cells).double()
+        chi2 = float(((counts - pairs / cells) ** 2).sum() / (pairs / cells))
+        assert abs(chi2 - (cells - 1)) < 5 * math.sqrt(2 * (cells - 1)), (name, chi2)
+    joint = torch.bincount(((u1 * 64).long().clamp_(0, 63) * 64 + (u2 * 64).long().clamp_(0, 63)).ravel(), minlength=4096).double()
+    chi2 = float(((joint - pairs / 4096) ** 2).sum() / (pairs / 4096))
+    assert abs(chi2 - 4095) < 5 * math.sqrt(2 * 4095), ("joint", chi2)
+    for lag in (1, 2, 3, 4, 5):  # 1: within a pair and across pairs, 2-3: across the pairs of a block, 4-5: across blocks
+        c = float((z[lag:] * z[:-lag]).mean())
+        assert abs(c) < 5 / math.sqrt((rows - lag) * cols), (lag, c)
+    c = float((z[:, 1:] * z[:, :-1]).mean())
+    assert abs(c) < 5 / math.sqrt(rows * (cols - 1))
