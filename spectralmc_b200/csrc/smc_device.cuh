@@ -108,8 +108,20 @@ constexpr uint32_t F32_REFINE_BIT = 0x80000000u;
 // normal (j % G) * rows + i of it, so a block's six normals are all consumed (oracle/philox.py).
 constexpr uint32_t F32_SHORT_BIT = 0x40000000u;
 
+#ifndef SMC_LOP3_REG
+#define SMC_LOP3_REG 1
+#endif
 __device__ __forceinline__ float unit_float_21(uint32_t field_in_bits_22_2) {
+#if SMC_LOP3_REG
+  // (v & mask) | one as ONE LOP3: the instruction takes a single immediate, so the exponent word has to sit in a register —
+  // ptxas never puts it there by itself (it emits AND-immediate + OR-immediate: 24 of the 76 ALU instructions per 12 normals).
+  uint32_t one, d;
+  asm("mov.b32 %0, 0x3f800000;" : "=r"(one));
+  asm("lop3.b32 %0, %1, 0x007ffffc, %2, 0xEA;" : "=r"(d) : "r"(field_in_bits_22_2), "r"(one));
+  return __uint_as_float(d);  // 1 + F 2^-21
+#else
   return __uint_as_float((field_in_bits_22_2 & 0x007ffffcu) | 0x3f800000u);  // 1 + F 2^-21
+#endif
 }
 
 __device__ __forceinline__ void box_muller_f32(float u1, float angle_unit, float& z_even, float& z_odd) {
@@ -339,12 +351,24 @@ __device__ __forceinline__ int sincos_reduced_f64(double d, double& s0, double& 
   return static_cast<int>(n);
 }
 
+// (v & mask) | bits as ONE LOP3 with `bits` in a register (see unit_float_21)
+template <uint32_t MASK, uint32_t BITS>
+__device__ __forceinline__ uint32_t and_or_bits(uint32_t v) {
+#if SMC_LOP3_REG
+  uint32_t bits, d;
+  asm("mov.b32 %0, %1;" : "=r"(bits) : "n"(BITS));
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(v), "n"(MASK), "r"(bits));
+  return d;
+#else
+  return (v & MASK) | BITS;
+#endif
+}
 __device__ __forceinline__ double f64_radius(uint32_t w0, uint32_t w1) {
-  const uint32_t lo = (__funnelshift_l(w1, w0, 20) & 0xfffffe00u) | 0x100u;
+  const uint32_t lo = and_or_bits<0xfffffe00u, 0x100u>(__funnelshift_l(w1, w0, 20));
   return radius_f64(__hiloint2double(static_cast<int>((w0 >> 12) | 0x3ff00000u), static_cast<int>(lo)));
 }
 __device__ __forceinline__ double f64_angle(uint32_t w1) {  // 1 + u2
-  return __hiloint2double(static_cast<int>(((w1 >> 1) & 0x000fffffu) | 0x3ff00000u), static_cast<int>((w1 << 31) | 0x40000000u));
+  return __hiloint2double(static_cast<int>(and_or_bits<0x000fffffu, 0x3ff00000u>(w1 >> 1)), static_cast<int>((w1 << 31) | 0x40000000u));
 }
 
 // (sin(pi y) / y - pi) / y^2 on |y| <= 1/2, degree 7 in y^2 (interpolated at the Chebyshev nodes with 50-digit arithmetic;
