@@ -135,6 +135,21 @@ __device__ __forceinline__ void box_muller_f32(float u1, float angle_unit, float
   z_odd = r * mufu_sin(theta);
 }
 
+#ifndef SMC_SHL_ALU
+#define SMC_SHL_ALU 0
+#endif
+// x << n; SMC_SHL_ALU = 1 asks for the funnel-shift form (ALU pipe) instead of ptxas' IMAD.SHL (FMA-heavy pipe, where Philox lives)
+template <int N>
+__device__ __forceinline__ uint32_t shl_bits(uint32_t x) {
+#if SMC_SHL_ALU
+  uint32_t d;
+  asm("shf.l.clamp.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(0u), "r"(x), "n"(N));
+  return d;
+#else
+  return x << N;
+#endif
+}
+
 // the rare path: radius field of pair `p` was zero -> u = (m + 0.5) 2^-44, m = top 23 bits of
 // word p of the refinement block.  Everything is passed by value (registers): taking the address
 // of the kernel-parameter key block would force a local-memory copy in the caller.
@@ -188,16 +203,16 @@ __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint
 #endif
 #if SMC_BM_ORDER == 0
   box_muller_f32(u[0], unit_float_21(__funnelshift_l(x[3], x[0], 12)), z[0], z[1]);
-  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12)), z[2], z[3]);
-  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12)), z[4], z[5]);
+  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(shl_bits<10>(x[3]), x[1], 12)), z[2], z[3]);
+  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(shl_bits<20>(x[3]), x[2], 12)), z[4], z[5]);
 #elif SMC_BM_ORDER == 1
-  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12)), z[4], z[5]);
-  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12)), z[2], z[3]);
+  if (NPAIRS >= 3) box_muller_f32(u[2], unit_float_21(__funnelshift_l(shl_bits<20>(x[3]), x[2], 12)), z[4], z[5]);
+  if (NPAIRS >= 2) box_muller_f32(u[1], unit_float_21(__funnelshift_l(shl_bits<10>(x[3]), x[1], 12)), z[2], z[3]);
   box_muller_f32(u[0], unit_float_21(__funnelshift_l(x[3], x[0], 12)), z[0], z[1]);
 #else
   const float a0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
-  const float a1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
-  const float a2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
+  const float a1 = unit_float_21(__funnelshift_l(shl_bits<10>(x[3]), x[1], 12));
+  const float a2 = unit_float_21(__funnelshift_l(shl_bits<20>(x[3]), x[2], 12));
   box_muller_f32(u[0], a0, z[0], z[1]);
   if (NPAIRS >= 2) box_muller_f32(u[1], a1, z[2], z[3]);
   if (NPAIRS >= 3) box_muller_f32(u[2], a2, z[4], z[5]);
@@ -257,14 +272,13 @@ __device__ __forceinline__ float2 normals12_sum_f32x2(uint32_t col, uint32_t q, 
   uint32_t x[4], y[4];
   philox4x32_10(col, q, k_lo, k_hi, key, x);
   philox4x32_10(col, q + 1u, k_lo, k_hi, key, y);
-  min_word = min(min(min_word, x[0]), min(x[1], x[2]));
-  min_word = min(min(min_word, y[0]), min(y[1], y[2]));
+  min_word = min(min(min_word, min(min(x[0], x[1]), x[2])), min(min(y[0], y[1]), y[2]));  // three 3-input minima
   const float ax0 = unit_float_21(__funnelshift_l(x[3], x[0], 12));
-  const float ax1 = unit_float_21(__funnelshift_l(x[3] << 10, x[1], 12));
-  const float ax2 = unit_float_21(__funnelshift_l(x[3] << 20, x[2], 12));
+  const float ax1 = unit_float_21(__funnelshift_l(shl_bits<10>(x[3]), x[1], 12));
+  const float ax2 = unit_float_21(__funnelshift_l(shl_bits<20>(x[3]), x[2], 12));
   const float ay0 = unit_float_21(__funnelshift_l(y[3], y[0], 12));
-  const float ay1 = unit_float_21(__funnelshift_l(y[3] << 10, y[1], 12));
-  const float ay2 = unit_float_21(__funnelshift_l(y[3] << 20, y[2], 12));
+  const float ay1 = unit_float_21(__funnelshift_l(shl_bits<10>(y[3]), y[1], 12));
+  const float ay2 = unit_float_21(__funnelshift_l(shl_bits<20>(y[3]), y[2], 12));
   acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[0] >> 9), unit_float_21(y[0] >> 9)), make_float2(ax0, ay0), acc);
   acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[1] >> 9), unit_float_21(y[1] >> 9)), make_float2(ax1, ay1), acc);
   return box_muller_sum_f32x2(make_float2(unit_float_21(x[2] >> 9), unit_float_21(y[2] >> 9)), make_float2(ax2, ay2), acc);
