@@ -32,7 +32,9 @@
 extern "C" {
 #endif
 
-#define SMC_VERSION 102 /* 0.1.2 */
+/* 103: the float64 stream draws TWO Box-Muller pairs per Philox block (43-bit radius + 21-bit angle field per pair,
+ *      oracle/philox.py); float64 results of 102 and earlier are a different sample set.  The float32 streams are unchanged. */
+#define SMC_VERSION 103 /* 0.1.3 */
 
 enum smc_status {
   SMC_OK = 0,

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol() -> None:
 def test_version_and_error_string() -> None:
     from spectralmc_b200 import _cabi
 
-    assert _cabi.version() == 102
+    assert _cabi.version() == 103
     assert isinstance(_cabi.LIB.smc_last_error(), bytes)
 
 
