@@ -248,6 +248,20 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   return unpack_f32x2(d);
 }
 
+#ifndef SMC_RADIUS_LEA
+#define SMC_RADIUS_LEA 1
+#endif
+// The 21-bit radius field (top 21 bits of a word) as a float in [1, 2) with the field in the LOW mantissa bits: a shift and an
+// add of the exponent word, which is ONE instruction (LEA.HI) — the field at mantissa bits 22..2 (unit_float_21) takes a shift
+// and a LOP3.  The value is 1 + R 2^-23, a quarter of the scale; the callers that use it carry the factor 4 through the logarithm.
+__device__ __forceinline__ float radius_float_top21(uint32_t word) {
+#if SMC_RADIUS_LEA
+  return __uint_as_float((word >> 11) + 0x3f800000u);
+#else
+  return unit_float_21(word >> 9);
+#endif
+}
+
 // Two Box–Muller pairs at once, accumulated: acc += (z_even + z_odd) / sqrt(2) of pair A in lane x and of pair B in
 // lane y.  Only the SUM of a pair's two normals enters the log-Euler path, and
 //   r cos(theta) + r sin(theta) = sqrt(2) r sin(theta + pi / 4),
@@ -255,12 +269,22 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
 // kernel — and the pi / 4 rides in the constant of the FFMA that forms the angle.  The caller multiplies the path's
 // accumulated sum by sqrt(2) once.  (Same draws as box_muller_f32; the MUFU error per pair is that of one sine.)
 __device__ __forceinline__ float2 box_muller_sum_f32x2(float2 radius_unit, float2 angle_unit, float2 acc) {
+#if SMC_RADIUS_LEA
+  // radius_unit = 1 + R 2^-23 (radius_float_top21): u / 4 = (R + 0.5) 2^-23 exactly, and -2 ln u = -2 ln 2 (lg2(u / 4) + 2)
+  const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffffep-1f, -0x1.fffffep-1f));
+#else
   const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffff8p-1f, -0x1.fffff8p-1f));
+#endif
   // theta + pi / 4 = 2 pi angle_unit - (3 pi - 2 pi 2^-22) + pi / 4
   const float2 theta = fma_f32x2(angle_unit, make_float2(6.28318530717958648f, 6.28318530717958648f),
                                  make_float2(-8.639378299343817f, -8.639378299343817f));
+#if SMC_RADIUS_LEA
+  const float2 m = fma_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)), make_float2(-1.38629436111989062f, -1.38629436111989062f),
+                             make_float2(-2.77258872223978124f, -2.77258872223978124f));
+#else
   const float2 m = mul_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)),
                              make_float2(-1.38629436111989062f, -1.38629436111989062f));
+#endif
   const float2 r = make_float2(mufu_sqrt(m.x), mufu_sqrt(m.y));
   return fma_f32x2(r, make_float2(mufu_sin(theta.x), mufu_sin(theta.y)), acc);
 }
@@ -279,9 +303,9 @@ __device__ __forceinline__ float2 normals12_sum_f32x2(uint32_t col, uint32_t q, 
   const float ay0 = unit_float_21(__funnelshift_l(y[3], y[0], 12));
   const float ay1 = unit_float_21(__funnelshift_l(shl_bits<10>(y[3]), y[1], 12));
   const float ay2 = unit_float_21(__funnelshift_l(shl_bits<20>(y[3]), y[2], 12));
-  acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[0] >> 9), unit_float_21(y[0] >> 9)), make_float2(ax0, ay0), acc);
-  acc = box_muller_sum_f32x2(make_float2(unit_float_21(x[1] >> 9), unit_float_21(y[1] >> 9)), make_float2(ax1, ay1), acc);
-  return box_muller_sum_f32x2(make_float2(unit_float_21(x[2] >> 9), unit_float_21(y[2] >> 9)), make_float2(ax2, ay2), acc);
+  acc = box_muller_sum_f32x2(make_float2(radius_float_top21(x[0]), radius_float_top21(y[0])), make_float2(ax0, ay0), acc);
+  acc = box_muller_sum_f32x2(make_float2(radius_float_top21(x[1]), radius_float_top21(y[1])), make_float2(ax1, ay1), acc);
+  return box_muller_sum_f32x2(make_float2(radius_float_top21(x[2]), radius_float_top21(y[2])), make_float2(ax2, ay2), acc);
 }
 
 __device__ __forceinline__ void normals6_f32(uint32_t col, uint32_t q, uint32_t k_lo, uint32_t k_hi,
