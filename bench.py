@@ -59,7 +59,7 @@ WORKLOADS = {
 }
 # SASS-counted work of the fused kernels' inner loops; tests/test_bench_contract.py re-counts them from the built
 # library (cuobjdump) so that a kernel edit cannot silently invalidate the rooflines.
-F32_LOOP = {"kernel": "_ZN3smc11step_kernelIfLi0ELi0ELi0ELi0E", "instructions": 142, "mufu": 18, "normals": 12}
+F32_LOOP = {"kernel": "_ZN3smc11step_kernelIfLi0ELi0ELi0ELi0E", "instructions": 137, "mufu": 18, "normals": 12}
 F64_LOOP = {"kernel": "_ZN3smc11step_kernelIdLi0ELi0ELi0ELi1E", "instructions": 150, "fp64": 76, "normals": 4}
 ISSUE_SLOTS_PER_STEP = F32_LOOP["instructions"] / F32_LOOP["normals"]  # warp-instructions per path-step per lane
 XU_OPS_PER_STEP = F32_LOOP["mufu"] / F32_LOOP["normals"]              # LG2 + SQRT + SIN + COS per pair; log-sum variant

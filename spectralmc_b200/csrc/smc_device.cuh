@@ -124,6 +124,23 @@ __device__ __forceinline__ float unit_float_21(uint32_t field_in_bits_22_2) {
 #endif
 }
 
+#ifndef SMC_RADIUS_LEA
+#define SMC_RADIUS_LEA 1
+#endif
+// The 21-bit radius field (top 21 bits of a word) as a float in [1, 2) with the field in the LOW mantissa bits: a shift and an
+// add of the exponent word, which is ONE instruction (LEA.HI) — the field at mantissa bits 22..2 (unit_float_21) takes a shift
+// and a LOP3.  The value is 1 + R 2^-23, a quarter of the scale: the callers form the uniform as 4 f - (4 - 2^-22) = (R + 0.5) 2^-21
+// in one exact FFMA where they had one exact FADD, so every value downstream is bit-identical to the two-instruction form.
+// (Carrying the factor through the logarithm instead — lg2(u / 4) + 2 — loses MUFU.LG2's absolute-error regime near u = 1 and
+// cancels for small radii: tried, caught by tests/test_gpu_fused.py.)
+__device__ __forceinline__ float radius_float_top21(uint32_t word) {
+#if SMC_RADIUS_LEA
+  return __uint_as_float((word >> 11) + 0x3f800000u);
+#else
+  return unit_float_21(word >> 9);
+#endif
+}
+
 __device__ __forceinline__ void box_muller_f32(float u1, float angle_unit, float& z_even, float& z_odd) {
   // angle_unit = 1 + A 2^-21;  u2 - 0.5 = angle_unit - 1.5 + 2^-22;  theta = 2 pi (u2 - 0.5) in ONE
   // FFMA: 2 pi angle_unit - (3 pi - 2 pi 2^-22).  The product is < 4 pi, so theta carries an absolute
@@ -187,7 +204,11 @@ __device__ __forceinline__ void normals6_f32_impl(uint32_t col, uint32_t q, uint
   philox4x32_10(col, q, k_lo, k_hi, key, x);
   float u[3];
 #pragma unroll
+#if SMC_RADIUS_LEA
+  for (int p = 0; p < 3; ++p) u[p] = fmaf(radius_float_top21(x[p]), 4.0f, -0x1.fffffep+1f);  // 4 (1 + R 2^-23) - (4 - 2^-22) = (R + 0.5) 2^-21, exact
+#else
   for (int p = 0; p < 3; ++p) u[p] = unit_float_21(x[p] >> 9) - 0x1.fffff8p-1f;  // (R + 0.5) 2^-21
+#endif
   if (REFINE) {
     if (__builtin_expect(min(min(x[0], x[1]), x[2]) < 2048u, 0)) {
       const float3 f = refine_radius_uniforms(col, q, k_lo, k_hi, key.k0[0], key.k1[0], x[0], x[1], x[2], u[0], u[1], u[2]);
@@ -248,20 +269,6 @@ __device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
   return unpack_f32x2(d);
 }
 
-#ifndef SMC_RADIUS_LEA
-#define SMC_RADIUS_LEA 1
-#endif
-// The 21-bit radius field (top 21 bits of a word) as a float in [1, 2) with the field in the LOW mantissa bits: a shift and an
-// add of the exponent word, which is ONE instruction (LEA.HI) — the field at mantissa bits 22..2 (unit_float_21) takes a shift
-// and a LOP3.  The value is 1 + R 2^-23, a quarter of the scale; the callers that use it carry the factor 4 through the logarithm.
-__device__ __forceinline__ float radius_float_top21(uint32_t word) {
-#if SMC_RADIUS_LEA
-  return __uint_as_float((word >> 11) + 0x3f800000u);
-#else
-  return unit_float_21(word >> 9);
-#endif
-}
-
 // Two Box–Muller pairs at once, accumulated: acc += (z_even + z_odd) / sqrt(2) of pair A in lane x and of pair B in
 // lane y.  Only the SUM of a pair's two normals enters the log-Euler path, and
 //   r cos(theta) + r sin(theta) = sqrt(2) r sin(theta + pi / 4),
@@ -270,21 +277,16 @@ __device__ __forceinline__ float radius_float_top21(uint32_t word) {
 // accumulated sum by sqrt(2) once.  (Same draws as box_muller_f32; the MUFU error per pair is that of one sine.)
 __device__ __forceinline__ float2 box_muller_sum_f32x2(float2 radius_unit, float2 angle_unit, float2 acc) {
 #if SMC_RADIUS_LEA
-  // radius_unit = 1 + R 2^-23 (radius_float_top21): u / 4 = (R + 0.5) 2^-23 exactly, and -2 ln u = -2 ln 2 (lg2(u / 4) + 2)
-  const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffffep-1f, -0x1.fffffep-1f));
+  // radius_unit = 1 + R 2^-23 (radius_float_top21): u = 4 f - (4 - 2^-22) = (R + 0.5) 2^-21, exact
+  const float2 u = fma_f32x2(radius_unit, make_float2(4.0f, 4.0f), make_float2(-0x1.fffffep+1f, -0x1.fffffep+1f));
 #else
   const float2 u = add_f32x2(radius_unit, make_float2(-0x1.fffff8p-1f, -0x1.fffff8p-1f));
 #endif
   // theta + pi / 4 = 2 pi angle_unit - (3 pi - 2 pi 2^-22) + pi / 4
   const float2 theta = fma_f32x2(angle_unit, make_float2(6.28318530717958648f, 6.28318530717958648f),
                                  make_float2(-8.639378299343817f, -8.639378299343817f));
-#if SMC_RADIUS_LEA
-  const float2 m = fma_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)), make_float2(-1.38629436111989062f, -1.38629436111989062f),
-                             make_float2(-2.77258872223978124f, -2.77258872223978124f));
-#else
   const float2 m = mul_f32x2(make_float2(mufu_lg2(u.x), mufu_lg2(u.y)),
                              make_float2(-1.38629436111989062f, -1.38629436111989062f));
-#endif
   const float2 r = make_float2(mufu_sqrt(m.x), mufu_sqrt(m.y));
   return fma_f32x2(r, make_float2(mufu_sin(theta.x), mufu_sin(theta.y)), acc);
 }
