@@ -772,9 +772,9 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
 #pragma unroll
   for (int u = 0; u < G; ++u) acc[u] = 0.0, run[u] = 0.0f;
   auto put_of = [&](const float (&z)[6], int u) {
-    float state = SCHEME == SMC_LOG_EULER ? 0.0f : k.X0;
+    float state = SCHEME == SMC_LOG_EULER ? z[u * T] : k.X0;  // log-Euler: the sum starts AT the first normal (0 + z is not folded: -0)
 #pragma unroll
-    for (int i = 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
+    for (int i = SCHEME == SMC_LOG_EULER ? 1 : 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
     const float val = SCHEME == SMC_LOG_EULER ? k.X0 * mufu_ex2(fmaf(k.lin1, state, k.lin0)) : state;
     const float diff = k.K - val;
     return k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
