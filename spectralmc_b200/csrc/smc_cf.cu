@@ -751,6 +751,30 @@ static __device__ __noinline__ void exchange_collect(const TileParams& p, double
 // of the group; the host takes this form only when 256 G is a multiple of N, so that lane u of thread t
 // stays in ONE column, (g_first G + t G + u) mod N, for the whole tile.  The 256 G accumulators are then
 // folded to the N column sums of the tile in shared memory, in a fixed order.
+#ifndef SMC_SHORT_POSTHOC
+#define SMC_SHORT_POSTHOC 1
+#endif
+#ifndef SMC_SHORT_PIN
+#define SMC_SHORT_PIN 1
+#endif
+// the rare group with a zero radius field (6e-6 of the blocks): the same block with the refinement applied, out of line and
+// by value, so that the common path carries neither the test-and-call of the refinement nor the moves that set the call up
+struct Normals6 {
+  float z0, z1, z2, z3, z4, z5;
+};
+static __device__ __noinline__ Normals6 short_group_exact(uint32_t g, uint32_t k_lo, uint32_t k_hi, uint32_t seed_lo, uint32_t seed_hi) {
+  PhiloxKeys keys;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    keys.k0[r] = seed_lo + static_cast<uint32_t>(r) * PHILOX_W0;
+    keys.k1[r] = seed_hi + static_cast<uint32_t>(r) * PHILOX_W1;
+  }
+  float z[6];
+  uint32_t unused = 0;
+  normals6_f32_impl<true, 3>(g, F32_SHORT_BIT, k_lo, k_hi, keys, z, unused);
+  return Normals6{z[0], z[1], z[2], z[3], z[4], z[5]};
+}
+
 template <int SCHEME, int T>
 __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const SimConsts<float>& k, uint32_t k_lo, uint32_t k_hi,
                                                    int64_t row0, int64_t row1, double* __restrict__ dst, double* sm,
@@ -771,12 +795,20 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
   float run[G];
 #pragma unroll
   for (int u = 0; u < G; ++u) acc[u] = 0.0, run[u] = 0.0f;
+  // lin1 and -X0 multiply a per-path value in FFMAs whose addend is a uniform register too; an FFMA takes one uniform operand,
+  // and ptxas re-copies the other into a vector register at EVERY use (12 copies per block).  Pinning the two in vector registers
+  // once per tile removes the copies.
+  float lin1 = k.lin1, neg_x0 = -k.X0;
+#if SMC_SHORT_PIN
+  // (an identity shuffle: ptxas allocates uniform registers itself and sees through anything that is not a real per-lane instruction)
+  lin1 = __shfl_sync(0xffffffffu, lin1, threadIdx.x & 31);
+  neg_x0 = __shfl_sync(0xffffffffu, neg_x0, threadIdx.x & 31);
+#endif
   auto put_of = [&](const float (&z)[6], int u) {
     float state = SCHEME == SMC_LOG_EULER ? z[u * T] : k.X0;  // log-Euler: the sum starts AT the first normal (0 + z is not folded: -0)
 #pragma unroll
     for (int i = SCHEME == SMC_LOG_EULER ? 1 : 0; i < T; ++i) consume<float, SCHEME>(state, z[u * T + i], k);
-    const float val = SCHEME == SMC_LOG_EULER ? k.X0 * mufu_ex2(fmaf(k.lin1, state, k.lin0)) : state;
-    const float diff = k.K - val;
+    const float diff = SCHEME == SMC_LOG_EULER ? fmaf(mufu_ex2(fmaf(lin1, state, k.lin0)), neg_x0, k.K) : k.K - state;
     return k.df * (diff > 0.0f ? diff : 0.0f);  // gbm.py:473
   };
   const uint32_t g_stop = static_cast<uint32_t>(g_end);  // g_end <= 2^32 / G + 1
@@ -802,8 +834,17 @@ __device__ __forceinline__ void grouped_short_tile(const TileParams& p, const Si
   uint32_t g = static_cast<uint32_t>(g_first) + threadIdx.x;
   for (; g < g_stop; g += CF_BLOCK) {
     float z[6];
+#if SMC_SHORT_POSTHOC
+    uint32_t min_word = 0xffffffffu;
+    normals6_f32_impl<false, 3>(g, F32_SHORT_BIT, k_lo, k_hi, p.keys, z, min_word);
+    if (__builtin_expect(min_word < 2048u, 0)) {
+      const Normals6 e = short_group_exact(g, k_lo, k_hi, p.keys.k0[0], p.keys.k1[0]);
+      z[0] = e.z0, z[1] = e.z1, z[2] = e.z2, z[3] = e.z3, z[4] = e.z4, z[5] = e.z5;
+    }
+#else
     uint32_t unused = 0;
     normals6_f32_impl<true, 3>(g, F32_SHORT_BIT, k_lo, k_hi, p.keys, z, unused);
+#endif
     add_group(g, z);
     if (++pending >= SHORT_FLUSH) {
       pending = 0;
