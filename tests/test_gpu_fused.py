@@ -466,3 +466,49 @@ def test_engine_at_the_reference_memory_guard() -> None:
     too_big = build_simulation_params(timesteps=1, network_size=1001, batches_per_mc_run=1_000_000, threads_per_block=256,
                                       mc_seed=5, buffer_size=1, dtype=Precision.float32)
     assert isinstance(too_big, Failure)
+
+
+def _zero_radius_hits(seed: int, k: int, cols: int, row_groups) -> list[tuple[int, int, int]]:
+    """(row-group word, column, pair) of every float32 Box-Muller pair of matrix ``k`` with a zero radius field (the oracle's Philox)."""
+    j = np.arange(cols, dtype=np.uint32)[None, :]
+    q = np.asarray(row_groups, dtype=np.uint32)[:, None]
+    x = philox.philox4x32_10((j, q, k & 0xFFFFFFFF, k >> 32), (seed & 0xFFFFFFFF, seed >> 32))
+    radius, _ = philox.f32_fields(*x)
+    return [(int(q[a, 0]), int(b), pair) for pair in range(3) for a, b in zip(*np.nonzero(radius[pair] == 0))]
+
+
+@pytest.mark.parametrize("layout", ["general", "short"])
+def test_rare_refinement_path_of_the_fused_kernels(layout) -> None:
+    """A zero radius field (2^-21 per pair) sends the fused kernels down an out-of-line path — the whole path re-simulated
+    with the refinement (long paths), the group's block redone (short tile).  At oracle-sized shapes that path is almost never
+    taken, so this test LOOKS for such pairs with the oracle's Philox and runs the one batch row that contains each hit:
+    every path of the row is its own CF column, so a wrong refinement shows (the test also proves that it would)."""
+    seed, k = 2026, 11
+    if layout == "general":
+        T, N = 12, 128  # two row groups: one normal in twelve carries enough of the path for a changed radius to show
+        paths = sorted({col for _, col, _ in _zero_radius_hits(seed, k, 1 << 20, range(T // 6))})
+    else:  # T = 1: six adjacent paths share a block, pair p serves paths 6 g + 2 p and 6 g + 2 p + 1
+        T, N = 1, 16
+        paths = sorted({6 * g + 2 * pair for _, g, pair in _zero_radius_hits(seed, k, 1 << 22, [philox.F32_SHORT_BIT])})
+    assert paths, "no zero radius field found: enlarge the search"
+    row_contract = (100.0, 150.0, 1.0, 0.05, 0.0, 0.2)  # deep in the money: the payoff is linear in the terminal price
+    contract = ogbm.Contract(*row_contract)
+    checked = 0
+    for path in paths[:6]:
+        b = path // N
+        B_total = b + 2
+        got = _fused([row_contract], T, N, B_total, torch.float32, seed, k, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, batch_begin=b, batch_end=b + 1)[0]
+        z, rad = philox.normals_matrix(T, N * B_total, np.float32, seed, k, col_begin=b * N, col_end=(b + 1) * N, return_radius=True)
+        refined = rad > 5.39  # sqrt(-2 ln u) for u < 2^-21: only refined draws reach it
+        assert refined.any(), (layout, path)
+        # what a kernel that skipped the refinement would produce (radius of the unrefined uniform 2^-22)
+        z_coarse = np.where(refined, z * (math.sqrt(-2.0 * math.log(2.0**-22)) / np.maximum(rad, 1e-30)), z).astype(np.float32)
+        ref, _ = ogbm.simulate_fft(contract, z.copy(), N, scheme="log_euler", normalization="raw_paths")  # (the oracle steps in place)
+        coarse, _ = ogbm.simulate_fft(contract, z_coarse, N, scheme="log_euler", normalization="raw_paths")
+        ref = np.asarray(ref, dtype=np.complex128) / B_total  # one row of B_total: the shard's share of the batch mean
+        coarse = np.asarray(coarse, dtype=np.complex128) / B_total
+        tol = 1e-5
+        if rel_max(coarse, ref) > 20 * tol:  # this hit is visible (its radius moved enough): the kernel must follow the specification
+            assert rel_max(got, ref) <= tol, (layout, path, rel_max(got, ref), rel_max(coarse, ref))
+            checked += 1
+    assert checked, "no hit moved the result enough to be checked"
