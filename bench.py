@@ -62,7 +62,8 @@ WORKLOADS = {
 F32_LOOP = {"kernel": "_ZN3smc11step_kernelIfLi0ELi0ELi0ELi0E", "instructions": 137, "mufu": 18, "normals": 12}
 F64_LOOP = {"kernel": "_ZN3smc11step_kernelIdLi0ELi0ELi0ELi1E", "instructions": 150, "fp64": 76, "normals": 4}
 ISSUE_SLOTS_PER_STEP = F32_LOOP["instructions"] / F32_LOOP["normals"]  # warp-instructions per path-step per lane
-XU_OPS_PER_STEP = F32_LOOP["mufu"] / F32_LOOP["normals"]              # LG2 + SQRT + SIN + COS per pair; log-sum variant
+XU_OPS_PER_STEP = F32_LOOP["mufu"] / F32_LOOP["normals"]              # log-Euler sum loop: LG2 + SQRT + ONE SIN per Box-Muller pair = 1.5 per normal
+XU_OPS_PER_STEP_ALL_NORMALS = 2.0                                     # loops that need every normal (SIMPLE_EULER): LG2 + SQRT + SIN + COS per pair
 FP64_OPS_PER_STEP = F64_LOOP["fp64"] / F64_LOOP["normals"]            # DFMA + DMUL + DADD per float64 path-step
 
 
@@ -522,7 +523,8 @@ def secondary_workloads(_cabi, torch, dev, calib: dict, args) -> dict:
                            "roofline": {"bound": "xu", "frac": steps2 / (ms * 1e-3) * XU_OPS_PER_STEP / calib["mufu"], "unit": "of calibrated MUFU peak, whole step"}}
     ms, k = time_fused(1, c2["T"], c2["N"], c2["B"], torch.float32, _cabi.SMC_SIMPLE_EULER, _cabi.SMC_RAW, 10)
     out["c2_simple_euler"] = {"ms": ms, "path_steps_per_sec": steps2 / (ms * 1e-3), "kernels": k,
-                              "roofline": {"bound": "xu", "frac": steps2 / (ms * 1e-3) * XU_OPS_PER_STEP / calib["mufu"], "unit": "of calibrated MUFU peak, whole step"}}
+                              "roofline": {"bound": "xu", "frac": steps2 / (ms * 1e-3) * XU_OPS_PER_STEP_ALL_NORMALS / calib["mufu"],
+                                           "unit": "of calibrated MUFU peak, whole step (2 XU ops per path-step: this scheme needs every normal, so COS + SIN stay)"}}
     # the opt-in Philox4x32-7 stream (smc_stream_version 1): NOT the stream `value` is measured on — a different sample set
     ms, k = time_fused(1, c2["T"], c2["N"], c2["B"], torch.float32, _cabi.SMC_LOG_EULER, _cabi.SMC_RAW, 10, stream_version=_cabi.SMC_STREAM_PHILOX7)
     out["c2_philox7_opt_in"] = {"ms": ms, "path_steps_per_sec": steps2 / (ms * 1e-3), "kernels": k,
